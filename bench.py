@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""bench.py — the driver's benchmark contract for the hybrid-retrieval hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU baseline arm (rank 0 only)
+
+Workload (BASELINE.json configs[1]): 1,000,000 docs x 384-dim f32 unit rows, cosine top-100,
+single-query GEMV path.  A *step* submits QUERIES_PER_STEP independent single-query scans in one
+C-ABI call (each query is its own full pass over the matrix: one scan kernel launch per query).
+N > 1: the same fixed corpus is sharded by document over the N GPUs (strong scaling); every rank
+scans its shard, local top-k lists are all-gathered with NCCL and merged on device.
+
+Prints ONE JSON line on rank 0.  `value` = device-timed queries/s with queries resident in HBM;
+`e2e` = the same through the host-buffer C-ABI call (pinned host queries in, host results out);
+`roofline` = algorithmic bytes of one scan launch / its average duration vs the measured HBM
+copy bandwidth; `cpu_baseline` = the self-written CPU oracle (no reference implementation of
+this path exists: SURVEY.md §0) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DOCS, DIM, TOPK = 1_000_000, 384, 100
+QUERIES_PER_STEP = 16
+SEED = 20261018
+METRIC = "cosine top-100 queries/sec (single-query GEMV path, 1M x 384 f32)"
+UNIT = "queries/s"
+WORKLOAD = "configs[1]: 1M docs x 384-dim f32, single query, cosine top-100 (GEMV bandwidth path)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for i, nme in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _synth_rows_parallel(O, n, dim, threads):
+    """oracle rows, generated in parallel chunks (ctypes releases the GIL)."""
+    import numpy as np
+    out = np.empty((n, dim), dtype=np.float32)
+    chunk = (n + threads - 1) // threads
+
+    def work(t):
+        lo, hi = t * chunk, min(n, (t + 1) * chunk)
+        if lo < hi:
+            out[lo:hi] = O.synth_rows_f32(hi - lo, dim, seed=SEED, first=lo)
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out
+
+
+def cpu_baseline_leg(rows, budget_s=12.0):
+    """Times the oracle's multi-threaded f32 scan + top-k on this box's host cores, on a bounded
+    sample: as many full single-query passes over the same 1M x 384 matrix as fit the budget."""
+    import numpy as np
+    import oracle as O
+    threads = O.max_threads()
+    rng = np.random.RandomState(1)
+    q = rng.standard_normal((64, DIM)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    O.cosine_topk_f32_fast(rows, q[0], TOPK, threads)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        O.cosine_topk_f32_fast(rows, q[n % 64], TOPK, threads)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 2000:
+            break
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d full single-query passes over the 1M x 384 f32 matrix in %.1f s, %d OpenMP threads on '%s' "
+                      "(self-written CPU oracle; no reference implementation of this path exists)" % (n, dt, threads, _cpu_model()),
+            "gbs": n * N_DOCS * DIM * 4 / dt / 1e9}
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU arm.  The reference has no implementation of this path (SURVEY.md
+    §0) and is Rust (no toolchain here), so the arm times the oracle port on the host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle as O
+    threads = O.max_threads()
+    rows = _synth_rows_parallel(O, N_DOCS, DIM, threads)
+    rng = np.random.RandomState(1)
+    qper = 2  # bounded sample: 2 of the QUERIES_PER_STEP queries per step
+    q = rng.standard_normal((64, DIM)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    for w in range(max(args.warmup, 1)):
+        O.cosine_topk_f32_fast(rows, q[w % 64], TOPK, threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for j in range(qper):
+            O.cosine_topk_f32_fast(rows, q[(s * qper + j) % 64], TOPK, threads)
+    dt = time.perf_counter() - t0
+    val = args.steps * qper / dt
+    sample = ("%d steps x %d full single-query passes over the 1M x 384 f32 matrix, %d OpenMP threads on '%s'"
+              % (args.steps, qper, threads, _cpu_model()))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (counter-hash unit rows, seed 20261018)",
+        "config": {"workload": WORKLOAD, "queries_per_step": qper, "n_docs": N_DOCS, "dim": DIM, "k": TOPK,
+                   "note": "reference has no implementation of this path; CPU oracle port timed instead"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", type=int, default=None, help="cosine kernel variant override (0 ldg, 1 bulk)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import openintel_b200 as oi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- shard of the fixed corpus held by this rank (strong scaling) --------------------------
+    per = (N_DOCS + world - 1) // world
+    base = rank * per
+    n_local = max(0, min(N_DOCS, base + per) - base)
+    ix = oi.GpuIndex(n_docs=n_local, dim=DIM, dtype=oi.DTYPE_F32, device=local_rank, doc_base=base,
+                     max_k=TOPK, max_batch=QUERIES_PER_STEP)
+    ix.synth_embeddings(SEED)
+    if args.variant is not None:
+        ix.set_option("cosine_variant", args.variant)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.from_numpy(oi.GpuIndex.comm_unique_id().copy())
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        ix.comm_init(rank, world, uid.cpu().numpy())
+
+    # ---- queries: a pool of distinct unit vectors, identical on every rank ----------------------
+    n_pool = 64
+    g = torch.Generator().manual_seed(1234)
+    pool = torch.randn(n_pool, QUERIES_PER_STEP, DIM, generator=g, dtype=torch.float32)
+    pool = pool / pool.norm(dim=2, keepdim=True)
+    d_pool = pool.to(dev)
+    h_pool = pool.pin_memory()
+    d_ids = torch.empty(QUERIES_PER_STEP, TOPK, dtype=torch.int32, device=dev)
+    d_sc = torch.empty(QUERIES_PER_STEP, TOPK, dtype=torch.float32, device=dev)
+    h_ids = torch.empty(QUERIES_PER_STEP, TOPK, dtype=torch.int32).pin_memory()
+    h_sc = torch.empty(QUERIES_PER_STEP, TOPK, dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev(i):
+        ix.search_cosine_dev(d_pool[i % n_pool], QUERIES_PER_STEP, TOPK, d_ids, d_sc, stream)
+
+    def step_host(i):
+        ix.search_cosine(h_pool[i % n_pool], TOPK, h_ids, h_sc)
+
+    # ---- device-resident leg ("value") ------------------------------------------------------------
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ix.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ix.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_queries = args.steps * QUERIES_PER_STEP
+    value = n_queries / (ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers through the C ABI -------------------------------------------
+    for i in range(args.warmup):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    barrier()
+    e2e_value = n_queries / e2e_s
+
+    # ---- sanity outside the timed region: results are ranked lists of real docs -------------------
+    ids = h_ids.numpy().view(np.uint32)
+    sc = h_sc.numpy()
+    assert np.all(np.diff(sc, axis=1) <= 0) and ids.max() < N_DOCS, "bench result is not a ranked list"
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        scan_launches = args.steps * QUERIES_PER_STEP
+        bytes_per_launch = n_local * DIM * 4
+        avg_launch_s = ms * 1e-3 / scan_launches  # includes the per-step unpack/merge share: conservative
+        achieved = bytes_per_launch / avg_launch_s / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rows = ix.read_embeddings(0, n_local)  # bit-identical to the oracle's rows (tests/test_gpu_cosine.py)
+            cpu = cpu_baseline_leg(rows)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (counter-hash unit rows generated on device, seed 20261018; random unit queries)",
+            "config": {"workload": WORKLOAD, "queries_per_step": QUERIES_PER_STEP, "n_docs": N_DOCS, "dim": DIM, "k": TOPK,
+                       "parallelism": "doc-sharded x%d, NCCL all-gather of local top-k + device merge" % world if world > 1 else "1 GPU",
+                       "l2": "each query streams %.2f GB per GPU, larger than the 126 MB L2; no flush needed" % (bytes_per_launch / 1e9),
+                       "kernel_variant": ix_variant_name(args.variant)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": QUERIES_PER_STEP * DIM * 4,
+                    "d2h_bytes_per_step": QUERIES_PER_STEP * TOPK * 8, "timing": "wall clock around blocking C-ABI calls, max over ranks"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "kernel": "cosine_scan_*_kernel", "bytes_per_launch": bytes_per_launch,
+                         "avg_launch_us": avg_launch_s * 1e6,
+                         "note": "avg launch = timed region / scan launches (includes unpack + launch gaps)"},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    ix.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def ix_variant_name(v):
+    return {None: "default", 0: "ldg (128-bit direct loads)", 1: "bulk (cp.async.bulk + mbarrier ring)"}[v]
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+// api.cu — the extern "C" boundary of libopenintel_gpu.so (include/openintel_gpu.h).
+// Owns the index handle, validates arguments, sequences kernels on a stream, and turns every
+// failure into a status code + message.  No CPU fallback exists: without a CUDA device the
+// library refuses to create an index.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "handle.h"
+
+static thread_local std::string g_create_error;
+
+oi_status oi_index::fail(oi_status code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  err = buf;
+  return code;
+}
+
+#define OI_CK(call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return h->fail(e_ == cudaErrorMemoryAllocation ? OI_ERR_OUT_OF_MEMORY : OI_ERR_CUDA,       \
+                     "%s failed: %s", #call, cudaGetErrorString(e_));                            \
+  } while (0)
+
+#define OI_REQUIRE(cond, ...)                                   \
+  do {                                                          \
+    if (!(cond)) return h->fail(OI_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+static oi_status create_fail(oi_status code, const std::string &msg) {
+  g_create_error = msg;
+  return code;
+}
+
+extern "C" const char *oi_version(void) { return "openintel_gpu 0.1 (sm_100a; cosine scan + BM25 + RRF; no CPU fallback)"; }
+
+extern "C" const char *oi_last_error(const oi_index *h) {
+  if (!h) return g_create_error.c_str();
+  return h->err.c_str();
+}
+
+extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) {
+  if (!out) return create_fail(OI_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!desc || desc->struct_size != sizeof(oi_index_desc)) return create_fail(OI_ERR_INVALID_ARG, "bad oi_index_desc (struct_size mismatch)");
+  if (desc->dtype != OI_DTYPE_F32 && desc->dtype != OI_DTYPE_BF16) return create_fail(OI_ERR_INVALID_ARG, "dtype must be OI_DTYPE_F32 or OI_DTYPE_BF16");
+  const uint32_t esize = desc->dtype == OI_DTYPE_F32 ? 4 : 2;
+  if (desc->dim == 0 || (desc->dim * esize) % 16 != 0) return create_fail(OI_ERR_INVALID_ARG, "dim * sizeof(dtype) must be a non-zero multiple of 16 bytes");
+  if (desc->max_k == 0 || desc->max_k > OI_MAX_K) return create_fail(OI_ERR_INVALID_ARG, "max_k must be in 1..1024");
+  if (desc->max_batch == 0 || desc->max_batch > 65536) return create_fail(OI_ERR_INVALID_ARG, "max_batch must be in 1..65536");
+  if (desc->n_docs + desc->doc_base > 0xFFFFFFFEull) return create_fail(OI_ERR_INVALID_ARG, "doc ids must fit in u32 (doc_base + n_docs <= 2^32 - 2)");
+
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return create_fail(OI_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+  if (desc->device < 0 || desc->device >= n_dev) return create_fail(OI_ERR_INVALID_ARG, "device ordinal out of range");
+
+  oi_index *h = new (std::nothrow) oi_index();
+  if (!h) return create_fail(OI_ERR_OUT_OF_MEMORY, "host allocation failed");
+  h->desc = *desc;
+  auto bail = [&](const char *what, cudaError_t ce) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(ce);
+    oi_index_destroy(h);
+    return create_fail(ce == cudaErrorMemoryAllocation ? OI_ERR_OUT_OF_MEMORY : OI_ERR_CUDA, m);
+  };
+  if ((e = cudaSetDevice(desc->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, desc->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major != 10) {
+    oi_index_destroy(h);
+    return create_fail(OI_ERR_UNSUPPORTED, "this build targets sm_100a (B200) only");
+  }
+  h->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+
+  const size_t emb_bytes = (size_t)desc->n_docs * desc->dim * esize;
+  if (emb_bytes && (e = cudaMalloc(&h->d_emb, emb_bytes)) != cudaSuccess) return bail("cudaMalloc(embeddings)", e);
+
+  const size_t B = desc->max_batch, K = desc->max_k;
+  h->cws.max_grid = oi_cosine_scan_max_grid(h->num_sms);
+  h->cws.k_stride = desc->max_k;
+  // the single-query scan runs one launch per query: candidate slots for min(B, 64) queries
+  // are enough because launches on one stream run back to back and each re-arms its slot
+  h->cws_slots = B;
+  if ((e = cudaMalloc(&h->cws.cand, h->cws_slots * h->cws.max_grid * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(cand)", e);
+  if ((e = cudaMalloc(&h->cws.gthr, B * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(gthr)", e);
+  if ((e = cudaMalloc(&h->cws.ticket, B * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(ticket)", e);
+  if ((e = cudaMemset(h->cws.gthr, 0, B * sizeof(u64))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMemset(h->cws.ticket, 0, B * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMalloc(&h->d_queries, B * desc->dim * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(queries)", e);
+  if ((e = cudaMalloc(&h->d_keys_cos, B * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
+  if ((e = cudaMalloc(&h->d_keys_bm25, B * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
+  if ((e = cudaMalloc(&h->d_out_u32, 3 * B * K * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(out)", e);
+  if ((e = cudaMalloc(&h->d_out_f32, B * K * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(out)", e);
+  *out = h;
+  return OI_OK;
+}
+
+extern "C" void oi_index_destroy(oi_index *h) {
+  if (!h) return;
+  cudaSetDevice(h->desc.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  oi_comm_destroy(h);
+  oi_bm25_free(h);
+  cudaFree(h->d_emb);
+  cudaFree(h->cws.cand);
+  cudaFree(h->cws.gthr);
+  cudaFree(h->cws.ticket);
+  cudaFree(h->d_queries);
+  cudaFree(h->d_keys_cos);
+  cudaFree(h->d_keys_bm25);
+  cudaFree(h->d_out_u32);
+  cudaFree(h->d_out_f32);
+  cudaFree(h->d_gather);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" uint64_t oi_index_launch_count(const oi_index *h) { return h ? h->launches : 0; }
+
+extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t value) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OI_REQUIRE(name != nullptr, "option name is NULL");
+  if (!strcmp(name, "cosine_variant")) {
+    OI_REQUIRE(value == 0 || value == 1, "cosine_variant must be 0 (ldg) or 1 (bulk pipeline)");
+    h->cosine_variant = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "bm25_variant")) {
+    h->bm25_variant = (int)value;
+    return OI_OK;
+  }
+  return h->fail(OI_ERR_INVALID_ARG, "unknown option '%s'", name);
+}
+
+// ---- embeddings -------------------------------------------------------------------------------
+extern "C" oi_status oi_index_load_embeddings(oi_index *h, const void *rows, uint64_t first_doc, uint64_t n) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OI_REQUIRE(rows != nullptr || n == 0, "rows is NULL");
+  OI_REQUIRE(first_doc + n <= h->desc.n_docs, "rows [%llu, %llu) outside the shard (n_docs = %llu)",
+             (unsigned long long)first_doc, (unsigned long long)(first_doc + n), (unsigned long long)h->desc.n_docs);
+  OI_CK(cudaSetDevice(h->desc.device));
+  const size_t row_bytes = (size_t)h->desc.dim * h->esize();
+  if (n) OI_CK(cudaMemcpyAsync((char *)h->d_emb + first_doc * row_bytes, rows, n * row_bytes, cudaMemcpyHostToDevice, h->stream));
+  OI_CK(cudaStreamSynchronize(h->stream));
+  h->emb_rows_loaded += n;
+  return OI_OK;
+}
+
+extern "C" oi_status oi_index_synth_embeddings(oi_index *h, uint64_t seed) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OI_CK(cudaSetDevice(h->desc.device));
+  OI_CK(oi_launch_synth_embeddings(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, seed, 0, h->desc.doc_base, h->stream, &h->launches));
+  OI_CK(cudaStreamSynchronize(h->stream));
+  h->emb_rows_loaded = h->desc.n_docs;
+  return OI_OK;
+}
+
+extern "C" oi_status oi_index_read_embeddings(oi_index *h, void *rows, uint64_t first_doc, uint64_t n) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OI_REQUIRE(rows != nullptr || n == 0, "rows is NULL");
+  OI_REQUIRE(first_doc + n <= h->desc.n_docs, "rows outside the shard");
+  OI_CK(cudaSetDevice(h->desc.device));
+  const size_t row_bytes = (size_t)h->desc.dim * h->esize();
+  if (n) OI_CK(cudaMemcpyAsync(rows, (const char *)h->d_emb + first_doc * row_bytes, n * row_bytes, cudaMemcpyDeviceToHost, h->stream));
+  OI_CK(cudaStreamSynchronize(h->stream));
+  return OI_OK;
+}
+
+// ---- search -----------------------------------------------------------------------------------
+static oi_status check_search_args(oi_index *h, uint32_t nq, uint32_t k) {
+  OI_REQUIRE(k >= 1 && k <= h->desc.max_k, "k = %u outside 1..max_k (%u)", k, h->desc.max_k);
+  OI_REQUIRE(nq <= h->desc.max_batch, "nq = %u exceeds max_batch (%u)", nq, h->desc.max_batch);
+  return OI_OK;
+}
+
+// local scan -> (multi-GPU: all-gather + merge) -> global cosine key lists in d_keys_cos
+static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, cudaStream_t st) {
+  if (h->emb_rows_loaded < h->desc.n_docs) return h->fail(OI_ERR_STATE, "embeddings not loaded (%llu of %llu rows)", (unsigned long long)h->emb_rows_loaded, (unsigned long long)h->desc.n_docs);
+  if (nq == 0) return OI_OK;
+  u64 *local = h->world > 1 ? h->d_keys_local : h->d_keys_cos;
+  OI_CK(oi_launch_cosine_scan(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, (uint32_t)h->desc.doc_base, d_queries, nq, k,
+                              h->cws, local, h->cosine_variant, h->num_sms, st, &h->launches));
+  if (h->world > 1) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_cos, st);
+  return OI_OK;
+}
+
+extern "C" oi_status oi_search_cosine_dev(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k,
+                                          uint32_t *d_out_ids, float *d_out_scores, void *cuda_stream) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  oi_status s = check_search_args(h, nq, k);
+  if (s) return s;
+  OI_REQUIRE(nq == 0 || (d_queries && d_out_ids && d_out_scores), "NULL device pointer");
+  OI_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if ((s = cosine_keys(h, d_queries, nq, k, st))) return s;
+  OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, d_out_ids, d_out_scores, st, &h->launches));
+  return OI_OK;
+}
+
+extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_t nq, uint32_t k,
+                                      uint32_t *out_ids, float *out_scores) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  oi_status s = check_search_args(h, nq, k);
+  if (s) return s;
+  OI_REQUIRE(nq == 0 || (queries && out_ids && out_scores), "NULL host pointer");
+  if (nq == 0) return OI_OK;
+  OI_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = h->stream;
+  OI_CK(cudaMemcpyAsync(h->d_queries, queries, (size_t)nq * h->desc.dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  if ((s = cosine_keys(h, h->d_queries, nq, k, st))) return s;
+  OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, h->d_out_u32, h->d_out_f32, st, &h->launches));
+  OI_CK(cudaMemcpyAsync(out_ids, h->d_out_u32, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaMemcpyAsync(out_scores, h->d_out_f32, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaStreamSynchronize(st));
+  return OI_OK;
+}

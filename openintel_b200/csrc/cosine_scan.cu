@@ -1,0 +1,522 @@
+// cosine_scan.cu — single-query cosine scan over the resident embedding matrix with the top-k
+// fused in (scores never reach HBM).  Bandwidth-bound GEMV: SURVEY.md §8d config 2.
+//
+//   algorithmic bytes per query = n_rows * dim * sizeof(T)        (roofline numerator)
+//
+// Two variants of the same contract:
+//   0  cosine_scan_ldg_kernel   one warp per row group, 128-bit ld.global.nc.L1::no_allocate,
+//                               ROWS x NVL independent loads in flight per lane, 2 CTAs / SM.
+//   1  cosine_scan_bulk_kernel  one producer warp streams row tiles with cp.async.bulk
+//                               (TMA 1-D, SASS UBLKCP) through an mbarrier ring in shared
+//                               memory; 8 consumer warps reduce rows from shared memory.
+// Both: warp-shuffle reduction per row, 64-bit (score, doc) keys (SPEC §1), a per-CTA candidate
+// buffer filtered by a running threshold (oi_common.cuh), a grid-wide threshold exchanged with
+// atomicMax, and a last-CTA merge of the per-CTA lists — one launch per query, no second kernel.
+#include <cuda_bf16.h>
+
+#include "internal.h"
+#include "oi_common.cuh"
+
+namespace {
+
+constexpr int kConsumerThreads = 256;
+constexpr int kConsumerWarps = kConsumerThreads / 32;
+
+// ---- element traits: a 16-byte vector holds QF elements ----------------------------------------
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static constexpr int QF = 4;
+  __device__ static __forceinline__ void load_q(const float *q, uint32_t v, float *out) {
+    float4 t = *reinterpret_cast<const float4 *>(q + (size_t)v * 4);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  }
+  __device__ static __forceinline__ float dot(uint4 d, const float *q, float acc) {
+    acc = fmaf(__uint_as_float(d.x), q[0], acc);
+    acc = fmaf(__uint_as_float(d.y), q[1], acc);
+    acc = fmaf(__uint_as_float(d.z), q[2], acc);
+    acc = fmaf(__uint_as_float(d.w), q[3], acc);
+    return acc;
+  }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static constexpr int QF = 8;
+  // SPEC §2 bf16 path: the query is rounded to bf16 (RNE) once, then used as f32
+  __device__ static __forceinline__ void load_q(const float *q, uint32_t v, float *out) {
+    float4 a = *reinterpret_cast<const float4 *>(q + (size_t)v * 8);
+    float4 b = *reinterpret_cast<const float4 *>(q + (size_t)v * 8 + 4);
+    float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = __bfloat162float(__float2bfloat16_rn(t[i]));
+  }
+  __device__ static __forceinline__ float dot(uint4 d, const float *q, float acc) {
+    acc = fmaf(__uint_as_float(d.x << 16), q[0], acc);
+    acc = fmaf(__uint_as_float(d.x & 0xFFFF0000u), q[1], acc);
+    acc = fmaf(__uint_as_float(d.y << 16), q[2], acc);
+    acc = fmaf(__uint_as_float(d.y & 0xFFFF0000u), q[3], acc);
+    acc = fmaf(__uint_as_float(d.z << 16), q[4], acc);
+    acc = fmaf(__uint_as_float(d.z & 0xFFFF0000u), q[5], acc);
+    acc = fmaf(__uint_as_float(d.w << 16), q[6], acc);
+    acc = fmaf(__uint_as_float(d.w & 0xFFFF0000u), q[7], acc);
+    return acc;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---- shared selection state of one CTA --------------------------------------------------------
+struct SelState {
+  u64 buf[OI_SEL_CAP];
+  u64 thr;
+  uint32_t cnt;
+  uint32_t is_last;
+};
+
+// Ends a scan CTA: final compaction, publish the sorted local list, and — in the last CTA to
+// arrive — merge all lists into out_keys.  Called by the `nthreads` threads of barrier `bar`.
+__device__ void scan_epilogue(SelState &S, const OiScanParams &p, int tid, int nthreads, int bar) {
+  const uint32_t k = p.k;
+  oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
+  if (tid == 0 && S.cnt == k) atomicMax(p.gthr, S.thr);
+  u64 *mine = p.cand + (size_t)blockIdx.x * k;
+  for (uint32_t i = tid; i < k; i += nthreads) mine[i] = i < S.cnt ? S.buf[i] : 0ull;
+  __threadfence();
+  oi_bar_sync(bar, nthreads);
+  if (tid == 0) {
+    uint32_t t = atomicAdd(p.ticket, 1u);
+    S.is_last = (t == gridDim.x - 1);
+  }
+  oi_bar_sync(bar, nthreads);
+  if (!S.is_last) return;
+  __threadfence();
+
+  // ---- last CTA: exact top-k of G sorted lists ---------------------------------------------
+  const uint32_t G = gridDim.x;
+  // (1) sampling bound: if m lists each hold >= ceil(k/m) keys >= T then >= k keys are >= T.
+  const uint32_t m = max(1u, G / 2);
+  const uint32_t j = (k + m - 1) / m - 1;
+  const uint32_t gp = oi_next_pow2(G);
+  for (uint32_t c = tid; c < gp; c += nthreads) S.buf[c] = c < G ? __ldcg(p.cand + (size_t)c * k + j) : 0ull;
+  oi_bar_sync(bar, nthreads);
+  oi_bitonic_desc(S.buf, gp, tid, nthreads, bar);
+  const u64 T = S.buf[m - 1];
+  oi_bar_sync(bar, nthreads);
+  if (tid == 0) { S.cnt = 0; S.thr = T > 0 ? T - 1 : 0; }
+  oi_bar_sync(bar, nthreads);
+  // (2) stream every candidate through the filter + buffer
+  const uint32_t total = G * k;
+  uint32_t base = 0;
+  while (base < total) {
+    // snapshot (cnt, thr) before anybody pushes: loop bounds must be CTA-uniform
+    const uint32_t span = min(total - base, (uint32_t)OI_SEL_CAP - S.cnt);
+    const u64 thr = S.thr;
+    oi_bar_sync(bar, nthreads);
+    for (uint32_t i = base + tid; i < base + span; i += nthreads) {
+      u64 key = __ldcg(p.cand + i);
+      if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+    }
+    base += span;
+    oi_bar_sync(bar, nthreads);
+    if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
+  }
+  // (3) emit and re-arm the per-query control words for the next launch
+  for (uint32_t i = tid; i < k; i += nthreads) p.out_keys[i] = i < S.cnt ? S.buf[i] : 0ull;
+  if (tid == 0) { *p.ticket = 0; *p.gthr = 0ull; }
+}
+
+// =================================================================================================
+// Variant 0: direct loads.  NVL = 16-byte vectors per lane per row (nv <= 32*NVL), ROWS rows in
+// flight per warp.
+// =================================================================================================
+template <typename T, int NVL, int ROWS>
+__global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_ldg_kernel(const OiScanParams p) {
+  constexpr int QF = Elem<T>::QF;
+  __shared__ SelState S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  float q[NVL][QF];
+#pragma unroll
+  for (int j = 0; j < NVL; ++j) {
+    const uint32_t v = lane + 32 * j;
+    if (v < p.nv) {
+      Elem<T>::load_q(p.q, v, q[j]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < QF; ++e) q[j][e] = 0.0f;
+    }
+  }
+  if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
+  __syncthreads();
+
+  const uint32_t row_begin = min(p.n_rows, blockIdx.x * p.rows_per_cta);
+  const uint32_t row_end = min(p.n_rows, row_begin + p.rows_per_cta);
+  const uint4 *mat = p.mat;
+  const uint32_t nv = p.nv;
+
+  uint32_t base = row_begin;
+  while (base < row_end) {
+    // super-iteration: at most (CAP - cnt) rows, so pushes cannot overflow the buffer
+    const uint32_t span = min(row_end - base, (uint32_t)OI_SEL_CAP - S.cnt);
+    const u64 thr = max(S.thr, ld_relaxed_u64(p.gthr));
+    const uint32_t stop = base + span;
+    __syncthreads();  // (cnt, thr) snapshot is CTA-uniform before anybody pushes
+    for (uint32_t r0 = base + warp * ROWS; r0 < stop; r0 += kConsumerWarps * ROWS) {
+      uint4 d[ROWS][NVL];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        const uint4 *rp = mat + (size_t)(r0 + i) * nv;
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+          const uint32_t v = lane + 32 * j;
+          d[i][j] = (r0 + i < stop && v < nv) ? oi_ldg_stream(rp + v) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      float acc[ROWS];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) a = Elem<T>::dot(d[i][j], q[j], a);
+        acc[i] = warp_sum(a);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          if (r0 + i < stop) {
+            u64 key = oi_make_key(acc[i], p.doc_base + r0 + i);
+            if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+          }
+        }
+      }
+    }
+    base = stop;
+    __syncthreads();
+    if (base < row_end && S.cnt > OI_SEL_CAP / 2) {
+      oi_sel_compact(S.buf, &S.cnt, &S.thr, p.k, tid, kConsumerThreads, 0);
+      if (tid == 0 && S.cnt == p.k) atomicMax(p.gthr, S.thr);
+    }
+  }
+  scan_epilogue(S, p, tid, kConsumerThreads, 0);
+}
+
+// Generic fallback for wide rows (nv > 256): the query lives in shared memory as f32.
+template <typename T>
+__global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_generic_kernel(const OiScanParams p) {
+  constexpr int QF = Elem<T>::QF;
+  extern __shared__ __align__(16) float s_q[];  // nv * QF floats
+  __shared__ SelState S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t v = tid; v < p.nv; v += kConsumerThreads) Elem<T>::load_q(p.q, v, s_q + (size_t)v * QF);
+  if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
+  __syncthreads();
+  const uint32_t row_begin = min(p.n_rows, blockIdx.x * p.rows_per_cta);
+  const uint32_t row_end = min(p.n_rows, row_begin + p.rows_per_cta);
+  uint32_t base = row_begin;
+  while (base < row_end) {
+    const uint32_t span = min(row_end - base, (uint32_t)OI_SEL_CAP - S.cnt);
+    const u64 thr = max(S.thr, ld_relaxed_u64(p.gthr));
+    const uint32_t stop = base + span;
+    __syncthreads();  // (cnt, thr) snapshot is CTA-uniform before anybody pushes
+    for (uint32_t r = base + warp; r < stop; r += kConsumerWarps) {
+      const uint4 *rp = p.mat + (size_t)r * p.nv;
+      float a0 = 0.0f, a1 = 0.0f;
+      uint32_t v = lane;
+      for (; v + 32 < p.nv; v += 64) {
+        uint4 d0 = oi_ldg_stream(rp + v), d1 = oi_ldg_stream(rp + v + 32);
+        a0 = Elem<T>::dot(d0, s_q + (size_t)v * QF, a0);
+        a1 = Elem<T>::dot(d1, s_q + (size_t)(v + 32) * QF, a1);
+      }
+      if (v < p.nv) a0 = Elem<T>::dot(oi_ldg_stream(rp + v), s_q + (size_t)v * QF, a0);
+      float s = warp_sum(a0 + a1);
+      if (lane == 0) {
+        u64 key = oi_make_key(s, p.doc_base + r);
+        if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+      }
+    }
+    base = stop;
+    __syncthreads();
+    if (base < row_end && S.cnt > OI_SEL_CAP / 2) {
+      oi_sel_compact(S.buf, &S.cnt, &S.thr, p.k, tid, kConsumerThreads, 0);
+      if (tid == 0 && S.cnt == p.k) atomicMax(p.gthr, S.thr);
+    }
+  }
+  scan_epilogue(S, p, tid, kConsumerThreads, 0);
+}
+
+// =================================================================================================
+// Variant 1: bulk-async-copy pipeline.  Warp 8 is the producer; warps 0-7 consume.
+// Dynamic smem: [n_stages][tile_bytes] row tiles (128 B aligned) then 2*n_stages mbarriers.
+// =================================================================================================
+template <typename T, int NVL>
+__global__ void __launch_bounds__(kConsumerThreads + 32, 1)
+    cosine_scan_bulk_kernel(const OiScanParams p, const uint32_t tile_rows, const uint32_t n_stages) {
+  constexpr int QF = Elem<T>::QF;
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ SelState S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t row_bytes = p.nv * 16u;
+  const uint32_t tile_bytes = tile_rows * row_bytes;
+  u64 *full = reinterpret_cast<u64 *>(s_dyn + (size_t)n_stages * tile_bytes);
+  u64 *empty = full + n_stages;
+
+  const uint32_t row_begin = min(p.n_rows, blockIdx.x * p.rows_per_cta);
+  const uint32_t row_end = min(p.n_rows, row_begin + p.rows_per_cta);
+  const uint32_t n_tiles = (row_end - row_begin + tile_rows - 1) / tile_rows;
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < n_stages; ++s) { oi_mbar_init(&full[s], 1); oi_mbar_init(&empty[s], kConsumerWarps); }
+    oi_mbar_fence_init();
+    S.cnt = 0; S.thr = 0ull;
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ---------------- producer: one elected lane streams the CTA's row range -----------------
+    if (lane == 0) {
+      const u64 policy = oi_policy_evict_first();
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(p.mat) + (size_t)row_begin * row_bytes;
+      for (uint32_t t = 0; t < n_tiles; ++t) {
+        const uint32_t s = t % n_stages, ph = (t / n_stages) & 1u;
+        oi_mbar_wait(&empty[s], ph ^ 1u);
+        const uint32_t rows = min(tile_rows, row_end - row_begin - t * tile_rows);
+        const uint32_t bytes = rows * row_bytes;
+        oi_mbar_expect_tx(&full[s], bytes);
+        oi_bulk_g2s(s_dyn + (size_t)s * tile_bytes, src + (size_t)t * tile_bytes, bytes, &full[s], policy);
+      }
+    }
+    return;  // the producer warp takes no part in barrier 1 or the epilogue
+  }
+
+  // -------------------------------- consumers --------------------------------------------------
+  float q[NVL][QF];
+#pragma unroll
+  for (int j = 0; j < NVL; ++j) {
+    const uint32_t v = lane + 32 * j;
+    if (v < p.nv) {
+      Elem<T>::load_q(p.q, v, q[j]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < QF; ++e) q[j][e] = 0.0f;
+    }
+  }
+
+  uint32_t t = 0;
+  while (t < n_tiles) {
+    // super-iteration over as many tiles as the candidate buffer can absorb in the worst case
+    const uint32_t tiles_now = min(n_tiles - t, max(1u, ((uint32_t)OI_SEL_CAP - S.cnt) / tile_rows));
+    const u64 thr = max(S.thr, ld_relaxed_u64(p.gthr));
+    oi_bar_sync(1, kConsumerThreads);  // (cnt, thr) snapshot is uniform before anybody pushes
+    for (uint32_t tt = t; tt < t + tiles_now; ++tt) {
+      const uint32_t s = tt % n_stages, ph = (tt / n_stages) & 1u;
+      const uint32_t tile_row0 = row_begin + tt * tile_rows;
+      const uint32_t rows = min(tile_rows, row_end - tile_row0);
+      oi_mbar_wait(&full[s], ph);
+      const unsigned char *tile = s_dyn + (size_t)s * tile_bytes;
+      for (uint32_t r = warp * 2; r < rows; r += kConsumerWarps * 2) {
+        const uint4 *rp0 = reinterpret_cast<const uint4 *>(tile + (size_t)r * row_bytes);
+        const bool two = r + 1 < rows;
+        const uint4 *rp1 = reinterpret_cast<const uint4 *>(tile + (size_t)(r + (two ? 1 : 0)) * row_bytes);
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+          const uint32_t v = lane + 32 * j;
+          if (v < p.nv) {
+            a0 = Elem<T>::dot(rp0[v], q[j], a0);
+            a1 = Elem<T>::dot(rp1[v], q[j], a1);
+          }
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) {
+          u64 k0 = oi_make_key(a0, p.doc_base + tile_row0 + r);
+          if (k0 > thr) oi_sel_push(S.buf, &S.cnt, k0);
+          if (two) {
+            u64 k1 = oi_make_key(a1, p.doc_base + tile_row0 + r + 1);
+            if (k1 > thr) oi_sel_push(S.buf, &S.cnt, k1);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) oi_mbar_arrive(&empty[s]);
+    }
+    t += tiles_now;
+    oi_bar_sync(1, kConsumerThreads);
+    if (t < n_tiles && S.cnt > OI_SEL_CAP / 2) {
+      oi_sel_compact(S.buf, &S.cnt, &S.thr, p.k, tid, kConsumerThreads, 1);
+      if (tid == 0 && S.cnt == p.k) atomicMax(p.gthr, S.thr);
+    }
+  }
+  scan_epilogue(S, p, tid, kConsumerThreads, 1);
+}
+
+// ---- host-side dispatch -------------------------------------------------------------------------
+template <typename T, int NVL, int ROWS>
+cudaError_t launch_ldg(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
+  cosine_scan_ldg_kernel<T, NVL, ROWS><<<grid, kConsumerThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t dispatch_ldg(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
+  const uint32_t nvl = (p.nv + 31) / 32;
+  switch (nvl) {
+    case 1: return launch_ldg<T, 1, 8>(p, grid, st);
+    case 2: return launch_ldg<T, 2, 4>(p, grid, st);
+    case 3: return launch_ldg<T, 3, 4>(p, grid, st);
+    case 4: return launch_ldg<T, 4, 2>(p, grid, st);
+    case 5:
+    case 6: return launch_ldg<T, 6, 2>(p, grid, st);
+    case 7:
+    case 8: return launch_ldg<T, 8, 1>(p, grid, st);
+    default: {
+      size_t smem = (size_t)p.nv * Elem<T>::QF * sizeof(float);
+      if (smem > 96 * 1024) return cudaErrorInvalidValue;
+      cudaError_t e = cudaFuncSetAttribute(cosine_scan_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      cosine_scan_generic_kernel<T><<<grid, kConsumerThreads, smem, st>>>(p);
+      return cudaGetLastError();
+    }
+  }
+}
+
+template <typename T, int NVL>
+cudaError_t launch_bulk(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
+  const uint32_t row_bytes = p.nv * 16u;
+  uint32_t tile_rows = (32768u / row_bytes) & ~7u;
+  if (tile_rows < 8) tile_rows = 8;
+  if (tile_rows > 256) tile_rows = 256;
+  const uint32_t tile_bytes = tile_rows * row_bytes;
+  const size_t budget = 200 * 1024;
+  uint32_t n_stages = (uint32_t)(budget / tile_bytes);
+  if (n_stages > 8) n_stages = 8;
+  if (n_stages < 2) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)n_stages * tile_bytes + 2 * n_stages * sizeof(u64);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(cosine_scan_bulk_kernel<T, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cosine_scan_bulk_kernel<T, NVL><<<grid, kConsumerThreads + 32, smem, st>>>(p, tile_rows, n_stages);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t dispatch_bulk(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
+  const uint32_t nvl = (p.nv + 31) / 32;
+  switch (nvl) {
+    case 1: return launch_bulk<T, 1>(p, grid, st);
+    case 2: return launch_bulk<T, 2>(p, grid, st);
+    case 3: return launch_bulk<T, 3>(p, grid, st);
+    case 4: return launch_bulk<T, 4>(p, grid, st);
+    case 5:
+    case 6: return launch_bulk<T, 6>(p, grid, st);
+    case 7:
+    case 8: return launch_bulk<T, 8>(p, grid, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+__global__ void unpack_keys_kernel(const u64 *keys, uint32_t n, uint32_t *ids, float *scores) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 key = keys[i];
+  ids[i] = key ? oi_key_doc(key) : OI_NO_DOC_U32;
+  scores[i] = key ? oi_key_score(key) : 0.0f;
+}
+
+// One CTA per query: exact top-k of world sorted lists (world * k <= a few thousand keys).
+__global__ void __launch_bounds__(256) merge_shards_kernel(const u64 *gathered, uint32_t world, uint32_t nq, uint32_t k, u64 *out) {
+  __shared__ SelState S;
+  const int tid = threadIdx.x;
+  const uint32_t qi = blockIdx.x;
+  if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
+  __syncthreads();
+  const uint32_t total = world * k;
+  uint32_t base = 0;
+  while (base < total) {
+    const uint32_t span = min(total - base, (uint32_t)OI_SEL_CAP - S.cnt);
+    const u64 thr = S.thr;
+    __syncthreads();
+    for (uint32_t i = base + tid; i < base + span; i += 256) {
+      const uint32_t r = i / k, j = i % k;
+      u64 key = gathered[((size_t)r * nq + qi) * k + j];
+      if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+    }
+    base += span;
+    __syncthreads();
+    if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
+  }
+  for (uint32_t i = tid; i < k; i += 256) out[(size_t)qi * k + i] = i < S.cnt ? S.buf[i] : 0ull;
+}
+
+}  // namespace
+
+uint32_t oi_cosine_scan_max_grid(int num_sms) { return (uint32_t)num_sms * 2u; }
+
+cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_rows, uint32_t dim,
+                                  uint32_t doc_base, const float *d_queries, uint32_t nq, uint32_t k,
+                                  const OiCosineWorkspace &ws, u64 *d_out_keys, int variant, int num_sms,
+                                  cudaStream_t stream, uint64_t *launches) {
+  const uint32_t esize = dtype == OI_DTYPE_F32 ? 4u : 2u;
+  OiScanParams p;
+  p.mat = reinterpret_cast<const uint4 *>(d_mat);
+  p.n_rows = (uint32_t)n_rows;
+  p.dim = dim;
+  p.nv = dim * esize / 16u;
+  p.doc_base = doc_base;
+  p.k = k;
+  // grid: one (bulk) or two (ldg) CTAs per SM, but never fewer than 64 rows per CTA
+  uint32_t grid = variant == 1 ? (uint32_t)num_sms : (uint32_t)num_sms * 2u;
+  const uint32_t max_useful = (uint32_t)((n_rows + 63) / 64);
+  if (grid > max_useful) grid = max_useful ? max_useful : 1;
+  if (grid > ws.max_grid) grid = ws.max_grid;
+  uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
+  rpc = (rpc + 31u) & ~31u;
+  p.rows_per_cta = rpc;
+  grid = (uint32_t)((n_rows + rpc - 1) / rpc);
+  if (grid == 0) grid = 1;
+  for (uint32_t qi = 0; qi < nq; ++qi) {
+    p.q = d_queries + (size_t)qi * dim;
+    p.cand = ws.cand + (size_t)qi * ws.max_grid * ws.k_stride;
+    p.gthr = ws.gthr + qi;
+    p.ticket = ws.ticket + qi;
+    p.out_keys = d_out_keys + (size_t)qi * k;
+    cudaError_t e;
+    if (variant == 1 && p.nv <= 256)
+      e = dtype == OI_DTYPE_F32 ? dispatch_bulk<float>(p, grid, stream) : dispatch_bulk<__nv_bfloat16>(p, grid, stream);
+    else
+      e = dtype == OI_DTYPE_F32 ? dispatch_ldg<float>(p, grid, stream) : dispatch_ldg<__nv_bfloat16>(p, grid, stream);
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t oi_launch_unpack_keys(const u64 *d_keys, uint32_t n, uint32_t *d_ids, float *d_scores,
+                                  cudaStream_t stream, uint64_t *launches) {
+  if (n == 0) return cudaSuccess;
+  unpack_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_keys, n, d_ids, d_scores);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t oi_launch_merge_shards(const u64 *d_gathered, uint32_t world, uint32_t nq, uint32_t k,
+                                   u64 *d_out, cudaStream_t stream, uint64_t *launches) {
+  if (nq == 0) return cudaSuccess;
+  merge_shards_kernel<<<nq, 256, 0, stream>>>(d_gathered, world, nq, k, d_out);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}

@@ -1,0 +1,49 @@
+// handle.h — the opaque oi_index: everything one shard owns on one GPU.
+#pragma once
+#include "internal.h"
+
+struct OiBm25;  // bm25.cu
+struct OiComm;  // comm.cu
+
+struct oi_index {
+  oi_index_desc desc{};
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;       // calls on one handle are serialised (SURVEY §8b threading)
+  std::string err;     // last error message
+  uint64_t launches = 0;
+
+  // embeddings
+  void *d_emb = nullptr;
+  uint64_t emb_rows_loaded = 0;
+  int cosine_variant = 0;
+
+  // per-call workspaces (device)
+  OiCosineWorkspace cws;
+  size_t cws_slots = 0;
+  float *d_queries = nullptr;     // [max_batch][dim]
+  u64 *d_keys_cos = nullptr;      // [max_batch][max_k] global cosine lists
+  u64 *d_keys_bm25 = nullptr;     // [max_batch][max_k] global BM25 lists
+  u64 *d_keys_local = nullptr;    // [max_batch][max_k] shard-local list before the all-gather
+  u64 *d_gather = nullptr;        // [world][max_batch][max_k]
+  uint32_t *d_out_u32 = nullptr;  // 3 x [max_batch][max_k]
+  float *d_out_f32 = nullptr;     // [max_batch][max_k]
+
+  // BM25
+  OiBm25 *bm25 = nullptr;
+  int bm25_variant = 0;
+
+  // multi-GPU
+  OiComm *comm = nullptr;
+  int rank = 0, world = 1;
+
+  uint32_t esize() const { return desc.dtype == OI_DTYPE_F32 ? 4u : 2u; }
+  oi_status fail(oi_status code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
+};
+
+// bm25.cu
+void oi_bm25_free(oi_index *h);
+// comm.cu
+void oi_comm_destroy(oi_index *h);
+// all-gathers each rank's [nq][k] local lists and merges them into d_out [nq][k] on every rank
+oi_status oi_comm_gather_merge(oi_index *h, const u64 *d_local, uint32_t nq, uint32_t k, u64 *d_out, cudaStream_t st);

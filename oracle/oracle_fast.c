@@ -21,15 +21,23 @@ int oio_max_threads(void) {
 #endif
 }
 
+typedef float v8f __attribute__((vector_size(32), aligned(4)));
+
+/* 4 independent 8-lane accumulators (AVX2 FMA): the scan should be limited by memory, not by
+ * the dependency chain of one accumulator */
 static inline float dot_f32(const float *restrict a, const float *restrict b, uint32_t dim) {
-  float acc[16];
-  for (int l = 0; l < 16; ++l) acc[l] = 0.0f;
+  v8f s0 = {0}, s1 = {0}, s2 = {0}, s3 = {0};
   uint32_t c = 0;
-  for (; c + 16 <= dim; c += 16)
-    for (int l = 0; l < 16; ++l) acc[l] += a[c + l] * b[c + l];
-  float s = 0.0f;
+  for (; c + 32 <= dim; c += 32) {
+    s0 += *(const v8f *)(a + c) * *(const v8f *)(b + c);
+    s1 += *(const v8f *)(a + c + 8) * *(const v8f *)(b + c + 8);
+    s2 += *(const v8f *)(a + c + 16) * *(const v8f *)(b + c + 16);
+    s3 += *(const v8f *)(a + c + 24) * *(const v8f *)(b + c + 24);
+  }
+  for (; c + 8 <= dim; c += 8) s0 += *(const v8f *)(a + c) * *(const v8f *)(b + c);
+  v8f t = (s0 + s1) + (s2 + s3);
+  float s = ((t[0] + t[4]) + (t[1] + t[5])) + ((t[2] + t[6]) + (t[3] + t[7]));
   for (; c < dim; ++c) s += a[c] * b[c];
-  for (int l = 0; l < 16; ++l) s += acc[l];
   return s;
 }
 

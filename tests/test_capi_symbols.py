@@ -1,0 +1,59 @@
+"""CPU-side boundary checks: the C-ABI library loads, exports every symbol include/openintel_gpu.h
+declares, and refuses to work without a GPU (no CPU fallback).  No compute call is made."""
+import os
+import re
+
+import pytest
+
+import openintel_b200 as oi
+from openintel_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "openintel_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(oi_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    return oi.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libopenintel_gpu.so does not export " + s
+    # and the binding declares a prototype for each of them
+    assert sorted(lib._oi_sig) == syms
+
+
+def test_version_and_no_cpu_fallback(lib):
+    assert "sm_100a" in oi.version()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device path cannot be exercised")
+    with pytest.raises(oi.OiError) as e:
+        oi.GpuIndex(n_docs=16, dim=64)
+    assert e.value.status == 2 and "no CPU fallback" in e.value.message
+
+
+def test_bad_descriptor_is_rejected_before_touching_cuda(lib):
+    for kw in (dict(dim=6), dict(dim=64, max_k=0), dict(dim=64, max_k=5000), dict(dim=64, dtype=9)):
+        args = dict(n_docs=16, dim=64)
+        args.update(kw)
+        with pytest.raises(oi.OiError) as e:
+            oi.GpuIndex(**args)
+        assert e.value.status == 1
+
+
+def test_missing_library_is_a_hard_error(monkeypatch, tmp_path):
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "_HERE", str(tmp_path))
+    with pytest.raises(OSError):
+        capi.load_library()

@@ -1,0 +1,126 @@
+"""GPU parity: cosine scan + fused top-k through the C ABI vs the CPU oracle (SPEC §2)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from gpu_util import assert_ranked_close
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL, BF16_TOL = 1e-5, 2e-3
+
+
+@pytest.fixture(scope="module")
+def oi():
+    import __graft_entry__ as ge
+    import openintel_b200
+    openintel_b200.load_library()
+    return openintel_b200
+
+
+def test_device_synth_is_bit_identical_to_oracle(oi):
+    for dim, dtype in ((384, oi.DTYPE_F32), (768, oi.DTYPE_BF16), (64, oi.DTYPE_F32)):
+        n = 3000
+        with oi.GpuIndex(n_docs=n, dim=dim, dtype=dtype, doc_base=1000) as ix:
+            ix.synth_embeddings(O.SEED)
+            got = ix.read_embeddings(0, n)
+        want = (O.synth_rows_f32 if dtype == oi.DTYPE_F32 else O.synth_rows_bf16)(n, dim, first=1000)
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,dim,k", [(50000, 384, 100), (20000, 768, 10), (4097, 128, 1), (9000, 1024, 100),
+                                     (3000, 2048, 7), (70000, 64, 1000)])
+def test_cosine_f32_parity(oi, variant, n, dim, k):
+    rows = O.synth_rows_f32(n, dim)
+    qs = np.concatenate([O.synth_rows_f32(2, dim, stream=1), O.synth_planted_queries(2, dim, n)[0]])
+    with oi.GpuIndex(n_docs=n, dim=dim, max_k=k, max_batch=4) as ix:
+        ix.load_embeddings(rows)
+        ix.set_option("cosine_variant", variant)
+        ids, sc = ix.search_cosine(qs, k)
+    for j in range(4):
+        allsc = O.cosine_scores_f32(rows, qs[j])
+        wi, ws, _ = O.topk_f64(allsc, k)
+        assert_ranked_close(ids[j], sc[j], wi, ws, allsc, F32_TOL)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,dim,k", [(40000, 768, 100), (10000, 384, 10), (5000, 1024, 50)])
+def test_cosine_bf16_parity(oi, variant, n, dim, k):
+    rows = O.synth_rows_bf16(n, dim)
+    qs = O.synth_rows_f32(3, dim, stream=1)
+    with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=3, doc_base=7) as ix:
+        ix.load_embeddings(rows)
+        ix.set_option("cosine_variant", variant)
+        ids, sc = ix.search_cosine(qs, k)
+    for j in range(3):
+        allsc = O.cosine_scores_bf16(rows, qs[j])
+        wi, ws, _ = O.topk_f64(allsc, k, doc_base=7)
+        assert_ranked_close(ids[j], sc[j], wi, ws, allsc, BF16_TOL, doc_base=7)
+        # measured error is far inside the budget
+        assert np.max(np.abs(sc[j] - ws)) < 1e-5
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_edge_cases(oi, variant):
+    dim = 64
+    # fewer docs than k -> padded with (NO_DOC, 0); exact ties broken by ascending doc id
+    rows = O.synth_rows_f32(5, dim)
+    rows[3] = rows[1]
+    with oi.GpuIndex(n_docs=5, dim=dim, max_k=8) as ix:
+        ix.load_embeddings(rows)
+        ix.set_option("cosine_variant", variant)
+        ids, sc = ix.search_cosine(rows[1:2], 8)
+        assert list(ids[0][:2]) == [1, 3] and sc[0][0] == sc[0][1]
+        assert list(ids[0][5:]) == [oi.NO_DOC] * 3 and list(sc[0][5:]) == [0.0] * 3
+        assert sorted(ids[0][:5]) == [0, 1, 2, 3, 4]
+        # nq = 0 is a no-op; k > max_k and unloaded state are errors
+        ix.search_cosine(np.zeros((0, dim), np.float32), 3)
+        with pytest.raises(oi.OiError) as e:
+            ix.search_cosine(rows[:1], 9)
+        assert e.value.status == 1
+    with oi.GpuIndex(n_docs=100, dim=dim, max_k=8) as ix:
+        with pytest.raises(oi.OiError) as e:
+            ix.search_cosine(rows[:1], 3)
+        assert e.value.status == 5
+    # all-identical rows: every score ties, order is by doc id
+    rows = np.tile(O.synth_rows_f32(1, dim), (5000, 1))
+    with oi.GpuIndex(n_docs=5000, dim=dim, max_k=100, doc_base=10) as ix:
+        ix.load_embeddings(rows)
+        ix.set_option("cosine_variant", variant)
+        ids, sc = ix.search_cosine(rows[:1], 100)
+        assert list(ids[0]) == list(range(10, 110))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_full_size_config2_properties(oi, variant):
+    """BASELINE config 2 (1M x 384 f32, top-100) through size-independent properties: planted
+    targets are found at rank 1, the list is sorted, ids are unique, and the result equals the
+    merge of the results of two half-size shards (checksum of checksums)."""
+    n, dim, k = 1_000_000, 384, 100
+    q, tgt = O.synth_planted_queries(2, dim, n)
+    q = np.concatenate([q, O.synth_rows_f32(1, dim, stream=1)])
+    with oi.GpuIndex(n_docs=n, dim=dim, max_k=k, max_batch=3) as ix:
+        ix.synth_embeddings(O.SEED)
+        ix.set_option("cosine_variant", variant)
+        ids, sc = ix.search_cosine(q, k)
+    assert ids[0][0] == tgt[0] and ids[1][0] == tgt[1] and sc[0][0] > 0.85
+    for j in range(3):
+        assert np.all(np.diff(sc[j]) <= 0) and len(set(ids[j])) == k
+    halves = []
+    for base in (0, n // 2):
+        with oi.GpuIndex(n_docs=n // 2, dim=dim, max_k=k, max_batch=3, doc_base=base) as ix:
+            ix.synth_embeddings(O.SEED)
+            ix.set_option("cosine_variant", variant)
+            halves.append(ix.search_cosine(q, k))
+    for j in range(3):
+        cat_ids = np.concatenate([halves[0][0][j], halves[1][0][j]])
+        cat_sc = np.concatenate([halves[0][1][j], halves[1][1][j]])
+        order = sorted(range(2 * k), key=lambda i: (-cat_sc[i], cat_ids[i]))[:k]
+        assert np.array_equal(cat_ids[order], ids[j]) and np.array_equal(cat_sc[order], sc[j])
+    # spot-check against the oracle on the rows that matter: recompute the reported docs' scores
+    for j in range(3):
+        for i in (0, 1, 50, 99):
+            row = O.synth_rows_f32(1, dim, first=int(ids[j][i]))
+            want = float(O.cosine_scores_f32(row, q[j])[0])
+            assert abs(want - sc[j][i]) <= F32_TOL * max(abs(want), 1e-2)
