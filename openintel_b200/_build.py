@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-ccbin", "/usr/bin/g++",
 ]
 # bm25.cu must keep one IEEE op per source op (SPEC §3): no FMA contraction there
-PER_FILE = {"bm25.cu": ["-fmad=false"]}
+PER_FILE = {"bm25.cu": ["-fmad=false"], "rrf.cu": ["-fmad=false"]}
 
 
 def _nvcc():

@@ -34,6 +34,8 @@ oi_status oi_index::fail(oi_status code, const char *fmt, ...) {
     if (!(cond)) return h->fail(OI_ERR_INVALID_ARG, __VA_ARGS__); \
   } while (0)
 
+void oi_set_thread_error(const std::string &msg) { g_create_error = msg; }
+
 static oi_status create_fail(oi_status code, const std::string &msg) {
   g_create_error = msg;
   return code;
@@ -226,6 +228,116 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
   OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, h->d_out_u32, h->d_out_f32, st, &h->launches));
   OI_CK(cudaMemcpyAsync(out_ids, h->d_out_u32, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaMemcpyAsync(out_scores, h->d_out_f32, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaStreamSynchronize(st));
+  return OI_OK;
+}
+
+// local BM25 lists -> (multi-GPU: all-gather + merge) -> global BM25 key lists in d_keys_bm25
+static oi_status bm25_keys(oi_index *h, const uint32_t *d_terms, const uint32_t *d_offs, uint32_t nq, uint32_t k, cudaStream_t st) {
+  if (nq == 0) return OI_OK;
+  u64 *local = h->world > 1 ? h->d_keys_local : h->d_keys_bm25;
+  oi_status s = oi_bm25_local_keys(h, d_terms, d_offs, nq, k, local, st);
+  if (s) return s;
+  if (h->world > 1) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_bm25, st);
+  return OI_OK;
+}
+
+// validates the host-side query term arrays and stages them on the device
+static oi_status stage_terms(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq, cudaStream_t st) {
+  if (!oi_bm25_stage_terms(h)) return h->fail(OI_ERR_STATE, "no BM25 index loaded");
+  OI_REQUIRE(q_offsets != nullptr, "q_offsets is NULL");
+  OI_REQUIRE(q_offsets[0] == 0, "q_offsets[0] must be 0");
+  for (uint32_t j = 0; j < nq; ++j) {
+    OI_REQUIRE(q_offsets[j + 1] >= q_offsets[j], "q_offsets not monotone at query %u", j);
+    OI_REQUIRE(q_offsets[j + 1] - q_offsets[j] <= 64, "query %u has %u terms (max 64)", j, q_offsets[j + 1] - q_offsets[j]);
+  }
+  const uint32_t total = q_offsets[nq];
+  OI_REQUIRE(total == 0 || q_terms != nullptr, "q_terms is NULL");
+  if (total) OI_CK(cudaMemcpyAsync(oi_bm25_stage_terms(h), q_terms, (size_t)total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  OI_CK(cudaMemcpyAsync(oi_bm25_stage_offs(h), q_offsets, ((size_t)nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  return OI_OK;
+}
+
+extern "C" oi_status oi_search_bm25_dev(oi_index *h, const uint32_t *d_q_terms, const uint32_t *d_q_offsets, uint32_t nq,
+                                        uint32_t k, uint32_t *d_out_ids, float *d_out_scores, void *cuda_stream) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  oi_status s = check_search_args(h, nq, k);
+  if (s) return s;
+  OI_REQUIRE(nq == 0 || (d_q_terms && d_q_offsets && d_out_ids && d_out_scores), "NULL device pointer");
+  OI_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if ((s = bm25_keys(h, d_q_terms, d_q_offsets, nq, k, st))) return s;
+  OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, d_out_ids, d_out_scores, st, &h->launches));
+  return OI_OK;
+}
+
+extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq,
+                                    uint32_t k, uint32_t *out_ids, float *out_scores) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  oi_status s = check_search_args(h, nq, k);
+  if (s) return s;
+  if (nq == 0) return OI_OK;
+  OI_REQUIRE(out_ids && out_scores, "NULL host pointer");
+  OI_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = h->stream;
+  if ((s = stage_terms(h, q_terms, q_offsets, nq, st))) return s;
+  if ((s = bm25_keys(h, oi_bm25_stage_terms(h), oi_bm25_stage_offs(h), nq, k, st))) return s;
+  OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, h->d_out_u32, h->d_out_f32, st, &h->launches));
+  OI_CK(cudaMemcpyAsync(out_ids, h->d_out_u32, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaMemcpyAsync(out_scores, h->d_out_f32, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaStreamSynchronize(st));
+  return OI_OK;
+}
+
+// cosine lists + BM25 lists (each global) -> RRF
+static oi_status hybrid_enqueue(oi_index *h, const float *d_queries, const uint32_t *d_terms, const uint32_t *d_offs,
+                                uint32_t nq, uint32_t k, uint32_t rrf_k, uint32_t *d_ids, float *d_rrf, uint32_t *d_rc,
+                                uint32_t *d_rb, cudaStream_t st) {
+  oi_status s;
+  if ((s = cosine_keys(h, d_queries, nq, k, st))) return s;
+  if ((s = bm25_keys(h, d_terms, d_offs, nq, k, st))) return s;
+  OI_CK(oi_launch_rrf(h->d_keys_cos, h->d_keys_bm25, nq, k, rrf_k, d_ids, d_rrf, d_rc, d_rb, st, &h->launches));
+  return OI_OK;
+}
+
+extern "C" oi_status oi_search_hybrid_dev(oi_index *h, const float *d_queries, const uint32_t *d_q_terms,
+                                          const uint32_t *d_q_offsets, uint32_t nq, uint32_t k, uint32_t rrf_k,
+                                          uint32_t *d_out_ids, float *d_out_rrf, uint32_t *d_out_rank_cos,
+                                          uint32_t *d_out_rank_bm25, void *cuda_stream) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  oi_status s = check_search_args(h, nq, k);
+  if (s) return s;
+  OI_REQUIRE(rrf_k >= 1 && rrf_k <= 1000000, "rrf_k = %u outside 1..1e6", rrf_k);
+  OI_REQUIRE(nq == 0 || (d_queries && d_q_terms && d_q_offsets && d_out_ids && d_out_rrf && d_out_rank_cos && d_out_rank_bm25), "NULL device pointer");
+  if (nq == 0) return OI_OK;
+  OI_CK(cudaSetDevice(h->desc.device));
+  return hybrid_enqueue(h, d_queries, d_q_terms, d_q_offsets, nq, k, rrf_k, d_out_ids, d_out_rrf, d_out_rank_cos, d_out_rank_bm25, (cudaStream_t)cuda_stream);
+}
+
+extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const uint32_t *q_terms, const uint32_t *q_offsets,
+                                      uint32_t nq, uint32_t k, uint32_t rrf_k, uint32_t *out_ids, float *out_rrf,
+                                      uint32_t *out_rank_cos, uint32_t *out_rank_bm25) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  oi_status s = check_search_args(h, nq, k);
+  if (s) return s;
+  OI_REQUIRE(rrf_k >= 1 && rrf_k <= 1000000, "rrf_k = %u outside 1..1e6", rrf_k);
+  if (nq == 0) return OI_OK;
+  OI_REQUIRE(queries && out_ids && out_rrf && out_rank_cos && out_rank_bm25, "NULL host pointer");
+  OI_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = h->stream;
+  const size_t n = (size_t)nq * k, BK = (size_t)h->desc.max_batch * h->desc.max_k;
+  OI_CK(cudaMemcpyAsync(h->d_queries, queries, (size_t)nq * h->desc.dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  if ((s = stage_terms(h, q_terms, q_offsets, nq, st))) return s;
+  uint32_t *d_ids = h->d_out_u32, *d_rc = h->d_out_u32 + BK, *d_rb = h->d_out_u32 + 2 * BK;
+  if ((s = hybrid_enqueue(h, h->d_queries, oi_bm25_stage_terms(h), oi_bm25_stage_offs(h), nq, k, rrf_k, d_ids, h->d_out_f32, d_rc, d_rb, st))) return s;
+  OI_CK(cudaMemcpyAsync(out_ids, d_ids, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaMemcpyAsync(out_rrf, h->d_out_f32, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaMemcpyAsync(out_rank_cos, d_rc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  OI_CK(cudaMemcpyAsync(out_rank_bm25, d_rb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaStreamSynchronize(st));
   return OI_OK;
 }

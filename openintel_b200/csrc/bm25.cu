@@ -1,0 +1,819 @@
+// bm25.cu — BM25 over a CSR inverted index (docs/SPEC.md §3): index load / on-device synthetic
+// build / weight folding, and the doc-range-blocked scoring kernel with the top-k fused in.
+//
+// Compiled with -fmad=false: SPEC §3 fixes ONE IEEE f32 operation per source-level operation,
+// in a fixed order, so that the GPU scores equal the oracle's bit for bit.
+//
+// Scoring kernel (bm25_blocked_kernel), the hot path of BASELINE config 3:
+//   * a work item is (query q, super-range s of documents); items are handed out from an atomic
+//     counter, s-major, so that the groups running at the same time walk the same part of every
+//     posting list and the second reader of a posting finds it in L1/L2 instead of HBM.
+//   * a *group* (32..512 threads of a 512-thread CTA) owns one item at a time.  It walks its
+//     super-range block by block (R documents per block); the block's scores live in shared
+//     memory (acc[R] f32), so the dense score vector never exists in HBM.
+//   * per block, the query's DISTINCT terms are applied in ascending term id (SPEC order).  A
+//     posting list holds a document at most once, so one term pass has no write conflicts and
+//     needs no atomics; passes are separated by a group barrier.  Posting lists are read as
+//     128-posting chunks (coalesced 4 B doc id + 4 B weight), software-pipelined one chunk ahead.
+//   * after the last term the group scans acc[] once: every positive score whose key beats the
+//     running threshold goes to the group's candidate buffer (filter + buffer selection, the
+//     same scheme as the cosine scan), acc[] is zeroed for the next block, and the k-th best key
+//     is published grid-wide (atomicMax) so later blocks of the same query filter harder.
+//   * the item ends with a sorted k-list per (query, super-range); bm25 merge = one CTA per
+//     query over the S lists.
+//
+//   algorithmic bytes per query = postings touched x 8 B (doc id + folded weight)
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cmath>
+#include <vector>
+
+#include "../../include/oi_synth_tables.h"
+#include "handle.h"
+#include "oi_common.cuh"
+#include "oi_synth.cuh"
+
+#define OI_BM25_MAX_QTERMS 64
+#define OI_BM25_ACC_FLOATS 32768  // 128 KB of block scores per CTA, split over the CTA's groups
+#define OI_BM25_THREADS 512
+#define OI_BM25_CHUNK 128         // postings per warp per step (4 x 32 lanes)
+
+struct OiBm25 {
+  uint32_t n_terms = 0;
+  uint64_t n_postings = 0;
+  u64 *d_term_off = nullptr;    // [n_terms + 1]
+  uint32_t *d_doc_ids = nullptr;  // [P] shard-local doc ids, ascending inside a list
+  uint32_t *d_tfs = nullptr;      // [P]
+  uint32_t *d_doc_len = nullptr;  // [n_docs]
+  float *d_w = nullptr;           // [P] folded weights (after finalize)
+  bool finalized = false;
+  // search workspace
+  uint32_t *d_qterms = nullptr;   // [max_batch][64] sorted distinct valid terms
+  uint32_t *d_qnt = nullptr;      // [max_batch]
+  u64 *d_gthr = nullptr;          // [max_batch]
+  uint32_t *d_counter = nullptr;  // item counter
+  u64 *d_lists = nullptr;         // [S][nq][k]
+  size_t lists_cap = 0;           // in (item) lists of max_k keys
+  uint32_t *d_in_terms = nullptr; // staging of the host call's flat term array [max_batch * 64]
+  uint32_t *d_in_offs = nullptr;  // [max_batch + 1]
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// group = the threads that own one work item.  One warp: __syncwarp; several warps: named barrier.
+// ------------------------------------------------------------------------------------------------
+struct Grp {
+  int tid;   // thread index inside the group
+  int size;  // threads in the group (multiple of 32)
+  int bar;   // named barrier id (1..15) for multi-warp groups
+  __device__ __forceinline__ void sync() const {
+    if (size == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(size) : "memory");
+  }
+};
+
+__device__ __forceinline__ void grp_bitonic_desc(u64 *buf, uint32_t n, const Grp &g) {
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = g.tid; i < (n >> 1); i += g.size) {
+        uint32_t l = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        uint32_t r = l | j;
+        u64 a = buf[l], b = buf[r];
+        bool desc = (l & k) == 0;
+        if ((a < b) == desc) { buf[l] = b; buf[r] = a; }
+      }
+      g.sync();
+    }
+  }
+}
+
+struct GrpCtl {
+  u64 thr;        // k-th best key seen by this item so far (0 = none)
+  uint32_t cnt;   // candidates in the buffer
+  uint32_t item;  // current work item
+  uint32_t aux;   // scratch counter (survivor count of a block)
+  uint32_t pad;
+};
+
+// keeps the best k of buf[0..cnt), sorted descending; raises thr when k are held
+__device__ __forceinline__ void grp_compact(u64 *buf, GrpCtl *ctl, uint32_t cap, uint32_t k, const Grp &g) {
+  uint32_t c = min(ctl->cnt, cap);
+  uint32_t n = oi_next_pow2(c);
+  g.sync();
+  for (uint32_t i = c + g.tid; i < n; i += g.size) buf[i] = 0ull;
+  g.sync();
+  grp_bitonic_desc(buf, n, g);
+  if (g.tid == 0) {
+    uint32_t keep = min(c, k);
+    ctl->cnt = keep;
+    if (keep == k && buf[k - 1] > ctl->thr) ctl->thr = buf[k - 1];
+  }
+  g.sync();
+}
+
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct Bm25Params {
+  const u64 *term_off;
+  const uint32_t *doc_ids;
+  const float *w;
+  const uint32_t *qterms;  // [nq][64]
+  const uint32_t *qnt;     // [nq]
+  u64 *gthr;               // [nq]
+  uint32_t *counter;
+  u64 *lists;              // [S][nq][k]
+  uint32_t n_docs, doc_base, nq, k;
+  uint32_t cap;            // candidate buffer keys per group (power of two, >= 2k)
+  uint32_t R;              // docs per block
+  uint32_t J;              // blocks per super-range
+  uint32_t S;              // super-ranges
+  uint32_t n_blocks;
+  uint32_t group_size;     // threads per group
+};
+
+// One warp applies its share of term postings [pos, e) that fall below doc id `bend`.
+// Chunks of 128 postings are dealt round-robin to the `n_warps` warps of the group (warp `wg`
+// takes chunks wg, wg + n_warps, ...).  Returns the number of in-block postings this warp applied.
+__device__ __forceinline__ uint32_t walk_term(const uint32_t *__restrict__ dids, const float *__restrict__ ws,
+                                              uint32_t pos, uint32_t e, uint32_t bbase, uint32_t bend,
+                                              float *acc, int wg, int n_warps, int lane) {
+  uint32_t total = 0;
+  uint32_t c = pos + (uint32_t)wg * OI_BM25_CHUNK;
+  uint32_t d[4];
+  float w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t p = c + 32 * j + lane;
+    const bool ok = p < e && p >= c;  // p >= c guards u32 wrap
+    d[j] = ok ? __ldg(dids + p) : 0xFFFFFFFFu;
+    w[j] = ok ? __ldg(ws + p) : 0.0f;
+  }
+  for (;;) {
+    // the chunk is entirely inside the block iff its last posting is
+    const bool full = __shfl_sync(0xFFFFFFFFu, d[3], 31) < bend;
+    if (full) {
+      const uint32_t cn = c + (uint32_t)n_warps * OI_BM25_CHUNK;
+      uint32_t d2[4];
+      float w2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // prefetch this warp's next chunk before touching shared memory
+        const uint32_t p = cn + 32 * j + lane;
+        const bool ok = p < e && p >= cn;
+        d2[j] = ok ? __ldg(dids + p) : 0xFFFFFFFFu;
+        w2[j] = ok ? __ldg(ws + p) : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float *a = acc + (d[j] - bbase);
+        *a = *a + w[j];  // SPEC §3: one f32 add, previous terms first
+      }
+      total += OI_BM25_CHUNK;
+      c = cn;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { d[j] = d2[j]; w[j] = w2[j]; }
+    } else {
+      uint32_t n = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in = d[j] < bend;
+        if (in) {
+          float *a = acc + (d[j] - bbase);
+          *a = *a + w[j];
+        }
+        n += __popc(__ballot_sync(0xFFFFFFFFu, in));
+      }
+      total += n;
+      break;
+    }
+  }
+  return total;
+}
+
+// dynamic shared memory layout (per CTA, NG = groups per CTA):
+//   float acc[OI_BM25_ACC_FLOATS]            NG slices of R floats
+//   u64   cand[NG][cap]
+//   u64   tbase[NG][64]      posting-array offset of each term's list
+//   u32   tcur[NG][64]       cursor inside the list (postings consumed so far)
+//   u32   tend[NG][64]       list length
+//   u32   tnxt[NG][64]       doc id at the cursor (0xFFFFFFFF = exhausted)
+//   GrpCtl ctl[NG]
+__global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const Bm25Params p) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int GS = (int)p.group_size;
+  const int NG = OI_BM25_THREADS / GS;
+  const int gi = threadIdx.x / GS;
+  Grp g;
+  g.tid = threadIdx.x % GS;
+  g.size = GS;
+  g.bar = 1 + gi;
+  const int lane = threadIdx.x & 31;
+  const int wg = g.tid >> 5, n_warps = GS >> 5;
+
+  float *acc_all = reinterpret_cast<float *>(s_dyn);
+  u64 *cand_all = reinterpret_cast<u64 *>(s_dyn + sizeof(float) * OI_BM25_ACC_FLOATS);
+  u64 *tbase_all = cand_all + (size_t)NG * p.cap;
+  uint32_t *tcur_all = reinterpret_cast<uint32_t *>(tbase_all + (size_t)NG * OI_BM25_MAX_QTERMS);
+  uint32_t *tend_all = tcur_all + NG * OI_BM25_MAX_QTERMS;
+  uint32_t *tnxt_all = tend_all + NG * OI_BM25_MAX_QTERMS;
+  GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(tnxt_all + NG * OI_BM25_MAX_QTERMS);
+
+  const uint32_t R = p.R;
+  float *acc = acc_all + (size_t)gi * R;
+  u64 *cand = cand_all + (size_t)gi * p.cap;
+  u64 *tbase = tbase_all + gi * OI_BM25_MAX_QTERMS;
+  uint32_t *tcur = tcur_all + gi * OI_BM25_MAX_QTERMS;
+  uint32_t *tend = tend_all + gi * OI_BM25_MAX_QTERMS;
+  uint32_t *tnxt = tnxt_all + gi * OI_BM25_MAX_QTERMS;
+  GrpCtl *ctl = ctl_all + gi;
+
+  for (uint32_t i = g.tid; i < R; i += GS) acc[i] = 0.0f;
+  const uint32_t n_items = p.S * p.nq;
+  const uint32_t k = p.k, cap = p.cap;
+
+  for (;;) {
+    g.sync();
+    if (g.tid == 0) ctl->item = atomicAdd(p.counter, 1u);
+    g.sync();
+    const uint32_t item = ctl->item;
+    if (item >= n_items) break;
+    const uint32_t s = item / p.nq, q = item % p.nq;
+    const uint32_t nt = p.qnt[q];
+    const uint32_t blk0 = s * p.J, blk1 = min(p.n_blocks, blk0 + p.J);
+    const uint32_t doc0 = blk0 * R;
+
+    // ---- item set-up: one binary search per term positions the cursor at the super-range start
+    for (uint32_t i = g.tid; i < nt; i += GS) {
+      const uint32_t t = p.qterms[(size_t)q * OI_BM25_MAX_QTERMS + i];
+      const u64 lo = p.term_off[t], hi = p.term_off[t + 1];
+      u64 a = lo, b = hi;
+      while (a < b) {
+        const u64 mid = a + ((b - a) >> 1);
+        if (__ldg(p.doc_ids + mid) < doc0) a = mid + 1; else b = mid;
+      }
+      tbase[i] = lo;
+      tcur[i] = (uint32_t)(a - lo);
+      tend[i] = (uint32_t)(hi - lo);
+      tnxt[i] = a < hi ? __ldg(p.doc_ids + a) : 0xFFFFFFFFu;
+    }
+    if (g.tid == 0) { ctl->cnt = 0; ctl->thr = 0ull; ctl->aux = 0; }
+    g.sync();
+
+    for (uint32_t blk = blk0; blk < blk1; ++blk) {
+      const uint32_t bbase = blk * R;
+      const uint32_t bend = min(p.n_docs, bbase + R);
+      // ---- term passes, ascending term id -------------------------------------------------------
+      bool touched = false;
+      for (uint32_t i = 0; i < nt; ++i) {
+        if (tnxt[i] >= bend) continue;  // group-uniform: this list has nothing in the block
+        touched = true;
+        const uint32_t pos = tcur[i], e = tend[i];
+        const u64 base = tbase[i];
+        const uint32_t n = walk_term(p.doc_ids + base, p.w + base, pos, e, bbase, bend, acc, wg, n_warps, lane);
+        g.sync();  // every read of tcur[i] and every add of this pass is done
+        if (lane == 0 && n) atomicAdd(&tcur[i], n);
+      }
+      if (!touched) continue;  // acc[] is still all zero
+      g.sync();
+      for (uint32_t i = g.tid; i < nt; i += GS) {
+        const uint32_t c = tcur[i];
+        if (tnxt[i] < bend) tnxt[i] = c < tend[i] ? __ldg(p.doc_ids + tbase[i] + c) : 0xFFFFFFFFu;
+      }
+      // ---- selection: positive scores that beat the running threshold -------------------------
+      const u64 thr = max(ctl->thr, ld_relaxed_u64(p.gthr + q));
+      const uint32_t span_all = bend - bbase;
+      const uint32_t cnt0 = ctl->cnt;
+      g.sync();
+      // optimistic pass: count first; in steady state only a handful survive
+      uint32_t mine = 0;
+      for (uint32_t j = g.tid; j < span_all; j += GS) {
+        const float sc = acc[j];
+        if (sc > 0.0f && oi_make_key(sc, p.doc_base + bbase + j) > thr) ++mine;
+      }
+      mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+      if (lane == 0 && mine) atomicAdd(&ctl->aux, mine);
+      g.sync();
+      const uint32_t survivors = ctl->aux;
+      g.sync();
+      if (g.tid == 0) ctl->aux = 0;
+      if (survivors <= cap - cnt0) {
+        if (survivors) {
+          for (uint32_t j = g.tid; j < span_all; j += GS) {
+            const float sc = acc[j];
+            if (sc > 0.0f) {
+              const u64 key = oi_make_key(sc, p.doc_base + bbase + j);
+              if (key > thr) { const uint32_t at = atomicAdd(&ctl->cnt, 1u); if (at < cap) cand[at] = key; }
+            }
+          }
+        }
+        g.sync();
+        if (ctl->cnt > cap / 2) {
+          grp_compact(cand, ctl, cap, k, g);
+          if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
+        }
+      } else {
+        // slow path (cold threshold): spans that cannot overflow the buffer, compacting between
+        uint32_t b0 = 0;
+        while (b0 < span_all) {
+          const uint32_t span = min(span_all - b0, cap - ctl->cnt);
+          const u64 t2 = max(thr, ctl->thr);
+          g.sync();
+          for (uint32_t j = b0 + g.tid; j < b0 + span; j += GS) {
+            const float sc = acc[j];
+            if (sc > 0.0f) {
+              const u64 key = oi_make_key(sc, p.doc_base + bbase + j);
+              if (key > t2) { const uint32_t at = atomicAdd(&ctl->cnt, 1u); if (at < cap) cand[at] = key; }
+            }
+          }
+          b0 += span;
+          g.sync();
+          if (ctl->cnt > cap / 2) {
+            grp_compact(cand, ctl, cap, k, g);
+            if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
+          }
+        }
+      }
+      for (uint32_t j = g.tid; j < span_all; j += GS) acc[j] = 0.0f;
+      g.sync();
+    }
+    // ---- item done: publish the sorted list ---------------------------------------------------
+    grp_compact(cand, ctl, cap, k, g);
+    if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
+    u64 *out = p.lists + ((size_t)s * p.nq + q) * k;
+    const uint32_t cnt = ctl->cnt;
+    for (uint32_t i = g.tid; i < k; i += GS) out[i] = i < cnt ? cand[i] : 0ull;
+  }
+}
+
+// sorts each query's terms ascending, drops duplicates, unknown terms and empty lists
+__global__ void bm25_prep_queries_kernel(const uint32_t *q_terms, const uint32_t *q_offs, uint32_t nq,
+                                         const u64 *term_off, uint32_t n_terms, uint32_t *out_terms,
+                                         uint32_t *out_nt, u64 *gthr, uint32_t *counter) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) *counter = 0;
+  if (q >= nq) return;
+  gthr[q] = 0ull;
+  uint32_t *o = out_terms + (size_t)q * OI_BM25_MAX_QTERMS;
+  const uint32_t lo = q_offs[q];
+  uint32_t n_in = q_offs[q + 1] - lo;
+  if (n_in > OI_BM25_MAX_QTERMS) n_in = OI_BM25_MAX_QTERMS;
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < n_in; ++i) {
+    const uint32_t t = q_terms[lo + i];
+    if (t >= n_terms || term_off[t + 1] == term_off[t]) continue;
+    // insertion into the sorted distinct prefix
+    uint32_t at = 0;
+    while (at < n && o[at] < t) ++at;
+    if (at < n && o[at] == t) continue;
+    for (uint32_t j = n; j > at; --j) o[j] = o[j - 1];
+    o[at] = t;
+    ++n;
+  }
+  out_nt[q] = n;
+}
+
+// per-posting folded weight, SPEC §3 association, one IEEE op per line (file built with -fmad=false)
+__global__ void bm25_weights_kernel(const u64 *term_off, const uint32_t *doc_ids, const uint32_t *tfs,
+                                    const uint32_t *doc_len, const float *idf, uint32_t n_terms, u64 n_postings,
+                                    float k1, float b, float avgdl, float *w) {
+  const float one_minus_b = 1.0f - b;
+  const float k1p1 = k1 + 1.0f;
+  for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < n_postings; p += (u64)gridDim.x * blockDim.x) {
+    // term of posting p: last t with term_off[t] <= p
+    uint32_t lo = 0, hi = n_terms;  // invariant: term_off[lo] <= p < term_off[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldg(term_off + mid) <= p) lo = mid; else hi = mid;
+    }
+    const float dl = (float)doc_len[doc_ids[p]];
+    const float ratio = dl / avgdl;
+    const float bt = b * ratio;
+    const float u = one_minus_b + bt;
+    const float norm = k1 * u;
+    const float tf = (float)tfs[p];
+    const float num = tf * k1p1;
+    const float den = tf + norm;
+    const float qv = num / den;
+    w[p] = idf[lo] * qv;
+  }
+}
+
+__global__ void sum_u32_kernel(const uint32_t *v, u64 n, u64 *out) {
+  u64 s = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+__global__ void df_from_offsets_kernel(const u64 *term_off, uint32_t n_terms, uint32_t *df) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_terms) df[t] = (uint32_t)(term_off[t + 1] - term_off[t]);
+}
+
+// ---- synthetic corpus (SPEC §9), bit-identical to oracle/oracle.c ------------------------------
+__constant__ uint16_t c_len_table[OI_LEN_TABLE_SIZE] = OI_LEN_TABLE_INIT;
+
+__global__ void synth_doc_len_kernel(uint64_t seed, uint64_t first_doc, uint64_t n_docs, uint32_t *doc_len) {
+  const uint64_t base = oi_stream_base(seed, 2);
+  for (u64 d = (u64)blockIdx.x * blockDim.x + threadIdx.x; d < n_docs; d += (u64)gridDim.x * blockDim.x)
+    doc_len[d] = c_len_table[oi_cell(oi_row_key(base, first_doc + d), 0) & (OI_LEN_TABLE_SIZE - 1)];
+}
+
+__device__ __forceinline__ uint32_t zipf_draw(uint64_t h, const double *__restrict__ cdf, uint32_t vocab) {
+  const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+  uint32_t lo = 0, hi = vocab - 1;
+  while (lo < hi) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (__ldg(cdf + mid) > u) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// One warp per document: draw the tokens, find the distinct terms and their multiplicities, append
+// (term << 32 | local doc, tf) pairs to a global array (order is fixed afterwards by a radix sort).
+__global__ void __launch_bounds__(256) synth_postings_kernel(uint64_t seed, uint64_t first_doc, uint64_t n_docs,
+                                                             const uint32_t *doc_len, const double *cdf, uint32_t vocab,
+                                                             u64 *keys, uint32_t *vals, u64 *n_out) {
+  __shared__ uint32_t s_tok[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t base = oi_stream_base(seed, 3);
+  for (u64 d = (u64)blockIdx.x * 8 + warp; d < n_docs; d += (u64)gridDim.x * 8) {
+    const uint32_t len = doc_len[d];
+    const uint64_t rk = oi_row_key(base, first_doc + d);
+    uint32_t *tok = s_tok[warp];
+    for (uint32_t i = lane; i < len; i += 32) tok[i] = zipf_draw(oi_cell(rk, i), cdf, vocab);
+    __syncwarp();
+    for (uint32_t i0 = 0; i0 < len; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      bool first = false;
+      uint32_t tf = 0, t = 0;
+      if (i < len) {
+        t = tok[i];
+        first = true;
+        for (uint32_t j = 0; j < len; ++j) {
+          const bool same = tok[j] == t;
+          tf += same;
+          if (same && j < i) first = false;
+        }
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, first);
+      u64 at = 0;
+      if (lane == 0 && m) at = atomicAdd(n_out, (u64)__popc(m));
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      if (first) {
+        const u64 o = at + __popc(m & ((1u << lane) - 1));
+        keys[o] = ((u64)t << 32) | (u64)d;
+        vals[o] = tf;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// sorted (term, doc) keys -> CSR arrays.  Thread i also closes the offsets of the terms between
+// its predecessor's term and its own.
+__global__ void csr_from_sorted_kernel(const u64 *keys, u64 n, uint32_t n_terms, u64 *term_off, uint32_t *doc_ids) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (u64)gridDim.x * blockDim.x) {
+    const long long t_cur = i < n ? (long long)(keys[i] >> 32) : (long long)n_terms;
+    const long long t_prev = i > 0 ? (long long)(keys[i - 1] >> 32) : -1;
+    for (long long t = t_prev + 1; t <= t_cur; ++t) term_off[t] = i;
+    if (i < n) doc_ids[i] = (uint32_t)keys[i];
+  }
+}
+
+unsigned grid_for(u64 n, int threads, int num_sms) {
+  u64 b = (n + threads - 1) / threads;
+  const u64 cap = (u64)num_sms * 16;
+  if (b > cap) b = cap;
+  return (unsigned)(b ? b : 1);
+}
+
+}  // namespace
+
+#define BM_CK(call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return h->fail(e_ == cudaErrorMemoryAllocation ? OI_ERR_OUT_OF_MEMORY : OI_ERR_CUDA,       \
+                     "%s failed: %s", #call, cudaGetErrorString(e_));                            \
+  } while (0)
+
+void oi_bm25_free(oi_index *h) {
+  OiBm25 *b = h->bm25;
+  if (!b) return;
+  cudaFree(b->d_term_off); cudaFree(b->d_doc_ids); cudaFree(b->d_tfs); cudaFree(b->d_doc_len); cudaFree(b->d_w);
+  cudaFree(b->d_qterms); cudaFree(b->d_qnt); cudaFree(b->d_gthr); cudaFree(b->d_counter); cudaFree(b->d_lists);
+  cudaFree(b->d_in_terms); cudaFree(b->d_in_offs);
+  delete b;
+  h->bm25 = nullptr;
+}
+
+static size_t bm25_lists_cap(const oi_index *h) { return (size_t)3 * h->num_sms * 16 + 64 + 2 * (size_t)h->desc.max_batch; }
+
+static oi_status bm25_alloc_workspace(oi_index *h, OiBm25 *b) {
+  const size_t B = h->desc.max_batch;
+  BM_CK(cudaMalloc(&b->d_qterms, B * OI_BM25_MAX_QTERMS * sizeof(uint32_t)));
+  BM_CK(cudaMalloc(&b->d_qnt, B * sizeof(uint32_t)));
+  BM_CK(cudaMalloc(&b->d_gthr, B * sizeof(u64)));
+  BM_CK(cudaMalloc(&b->d_counter, sizeof(uint32_t)));
+  b->lists_cap = bm25_lists_cap(h);
+  BM_CK(cudaMalloc(&b->d_lists, b->lists_cap * h->desc.max_k * sizeof(u64)));
+  BM_CK(cudaMalloc(&b->d_in_terms, B * OI_BM25_MAX_QTERMS * sizeof(uint32_t)));
+  BM_CK(cudaMalloc(&b->d_in_offs, (B + 1) * sizeof(uint32_t)));
+  return OI_OK;
+}
+
+extern "C" oi_status oi_index_load_bm25(oi_index *h, const uint64_t *term_offsets, const uint32_t *doc_ids,
+                                        const uint32_t *tfs, const uint32_t *doc_len, uint32_t n_terms) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!term_offsets || !doc_len || n_terms == 0) return h->fail(OI_ERR_INVALID_ARG, "NULL CSR array or n_terms == 0");
+  const uint64_t P = term_offsets[n_terms];
+  if (P && (!doc_ids || !tfs)) return h->fail(OI_ERR_INVALID_ARG, "NULL postings array");
+  if (term_offsets[0] != 0) return h->fail(OI_ERR_INVALID_ARG, "term_offsets[0] must be 0");
+  for (uint32_t t = 0; t < n_terms; ++t)
+    if (term_offsets[t + 1] < term_offsets[t]) return h->fail(OI_ERR_INVALID_ARG, "term_offsets not monotone at term %u", t);
+  for (uint32_t t = 0; t < n_terms; ++t)
+    for (uint64_t p = term_offsets[t]; p < term_offsets[t + 1]; ++p) {
+      if (doc_ids[p] >= h->desc.n_docs) return h->fail(OI_ERR_INVALID_ARG, "posting %llu: doc id %u outside the shard", (unsigned long long)p, doc_ids[p]);
+      if (p > term_offsets[t] && doc_ids[p] <= doc_ids[p - 1]) return h->fail(OI_ERR_INVALID_ARG, "term %u: doc ids must be strictly ascending inside a list", t);
+    }
+  BM_CK(cudaSetDevice(h->desc.device));
+  oi_bm25_free(h);
+  OiBm25 *b = new OiBm25();
+  h->bm25 = b;
+  b->n_terms = n_terms;
+  b->n_postings = P;
+  const size_t Pa = P ? P : 1;
+  BM_CK(cudaMalloc(&b->d_term_off, ((size_t)n_terms + 1) * sizeof(u64)));
+  BM_CK(cudaMalloc(&b->d_doc_ids, Pa * sizeof(uint32_t)));
+  BM_CK(cudaMalloc(&b->d_tfs, Pa * sizeof(uint32_t)));
+  BM_CK(cudaMalloc(&b->d_w, Pa * sizeof(float)));
+  BM_CK(cudaMalloc(&b->d_doc_len, (h->desc.n_docs ? h->desc.n_docs : 1) * sizeof(uint32_t)));
+  BM_CK(cudaMemcpyAsync(b->d_term_off, term_offsets, ((size_t)n_terms + 1) * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+  if (P) {
+    BM_CK(cudaMemcpyAsync(b->d_doc_ids, doc_ids, P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    BM_CK(cudaMemcpyAsync(b->d_tfs, tfs, P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (h->desc.n_docs) BM_CK(cudaMemcpyAsync(b->d_doc_len, doc_len, h->desc.n_docs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  BM_CK(cudaStreamSynchronize(h->stream));
+  return bm25_alloc_workspace(h, b);
+}
+
+extern "C" oi_status oi_index_synth_bm25(oi_index *h, uint64_t seed, uint32_t vocab, const double *zipf_cdf) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!zipf_cdf || vocab == 0) return h->fail(OI_ERR_INVALID_ARG, "zipf_cdf is NULL or vocab == 0");
+  BM_CK(cudaSetDevice(h->desc.device));
+  oi_bm25_free(h);
+  OiBm25 *b = new OiBm25();
+  h->bm25 = b;
+  b->n_terms = vocab;
+  const u64 n = h->desc.n_docs;
+  cudaStream_t st = h->stream;
+  double *d_cdf = nullptr;
+  u64 *d_cnt = nullptr, *d_keys = nullptr, *d_keys2 = nullptr;
+  uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
+  void *d_tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(d_cdf); cudaFree(d_cnt); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp); };
+#define SY_CK(call)                                                                                       \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      cleanup();                                                                                          \
+      return h->fail(e_ == cudaErrorMemoryAllocation ? OI_ERR_OUT_OF_MEMORY : OI_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    }                                                                                                     \
+  } while (0)
+  SY_CK(cudaMalloc(&d_cdf, (size_t)vocab * sizeof(double)));
+  SY_CK(cudaMemcpyAsync(d_cdf, zipf_cdf, (size_t)vocab * sizeof(double), cudaMemcpyHostToDevice, st));
+  SY_CK(cudaMalloc(&b->d_doc_len, (n ? n : 1) * sizeof(uint32_t)));
+  SY_CK(cudaMalloc(&d_cnt, 2 * sizeof(u64)));
+  SY_CK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(u64), st));
+  u64 h_cnt[2] = {0, 0};
+  if (n) {
+    synth_doc_len_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, st>>>(seed, h->desc.doc_base, n, b->d_doc_len);
+    sum_u32_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, st>>>(b->d_doc_len, n, d_cnt);
+    h->launches += 2;
+    SY_CK(cudaGetLastError());
+    SY_CK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    SY_CK(cudaStreamSynchronize(st));
+  }
+  const u64 n_tokens = h_cnt[0];
+  const size_t cap = n_tokens ? n_tokens : 1;
+  SY_CK(cudaMalloc(&d_keys, cap * sizeof(u64)));
+  SY_CK(cudaMalloc(&d_vals, cap * sizeof(uint32_t)));
+  if (n) {
+    u64 blocks = (n + 7) / 8;
+    if (blocks > (u64)h->num_sms * 32) blocks = (u64)h->num_sms * 32;
+    synth_postings_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, h->desc.doc_base, n, b->d_doc_len, d_cdf, vocab, d_keys, d_vals, d_cnt + 1);
+    ++h->launches;
+    SY_CK(cudaGetLastError());
+    SY_CK(cudaMemcpyAsync(h_cnt, d_cnt, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    SY_CK(cudaStreamSynchronize(st));
+  }
+  const u64 P = h_cnt[1];
+  b->n_postings = P;
+  const size_t Pa = P ? P : 1;
+  SY_CK(cudaMalloc(&d_keys2, Pa * sizeof(u64)));
+  SY_CK(cudaMalloc(&d_vals2, Pa * sizeof(uint32_t)));
+  int term_bits = 1;
+  while ((1ull << term_bits) < vocab) ++term_bits;
+  const u64 *sorted_keys = d_keys;
+  const uint32_t *sorted_vals = d_vals;
+  if (P) {
+    cub::DoubleBuffer<u64> kb(d_keys, d_keys2);
+    cub::DoubleBuffer<uint32_t> vb(d_vals, d_vals2);
+    size_t tmp_bytes = 0;
+    SY_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, P, 0, 32 + term_bits, st));
+    SY_CK(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    SY_CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, kb, vb, P, 0, 32 + term_bits, st));
+    h->launches += 8;
+    sorted_keys = kb.Current();
+    sorted_vals = vb.Current();
+  }
+  SY_CK(cudaMalloc(&b->d_term_off, ((size_t)vocab + 1) * sizeof(u64)));
+  SY_CK(cudaMalloc(&b->d_doc_ids, Pa * sizeof(uint32_t)));
+  SY_CK(cudaMalloc(&b->d_tfs, Pa * sizeof(uint32_t)));
+  SY_CK(cudaMalloc(&b->d_w, Pa * sizeof(float)));
+  csr_from_sorted_kernel<<<grid_for(P + 1, 256, h->num_sms), 256, 0, st>>>(sorted_keys, P, vocab, b->d_term_off, b->d_doc_ids);
+  ++h->launches;
+  SY_CK(cudaGetLastError());
+  if (P) SY_CK(cudaMemcpyAsync(b->d_tfs, sorted_vals, P * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  SY_CK(cudaStreamSynchronize(st));
+  cleanup();
+#undef SY_CK
+  return bm25_alloc_workspace(h, b);
+}
+
+extern "C" oi_status oi_index_bm25_local_stats(oi_index *h, uint32_t *df_out, uint64_t *sum_doc_len, uint64_t *n_postings) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OiBm25 *b = h->bm25;
+  if (!b) return h->fail(OI_ERR_STATE, "no BM25 index loaded");
+  BM_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = h->stream;
+  if (n_postings) *n_postings = b->n_postings;
+  if (df_out) {
+    uint32_t *d_df = nullptr;
+    BM_CK(cudaMalloc(&d_df, (size_t)b->n_terms * sizeof(uint32_t)));
+    df_from_offsets_kernel<<<(b->n_terms + 255) / 256, 256, 0, st>>>(b->d_term_off, b->n_terms, d_df);
+    ++h->launches;
+    cudaError_t e = cudaMemcpyAsync(df_out, d_df, (size_t)b->n_terms * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_df);
+    BM_CK(e);
+  }
+  if (sum_doc_len) {
+    u64 *d_s = nullptr;
+    BM_CK(cudaMalloc(&d_s, sizeof(u64)));
+    cudaError_t e = cudaMemsetAsync(d_s, 0, sizeof(u64), st);
+    if (e == cudaSuccess && h->desc.n_docs) {
+      sum_u32_kernel<<<grid_for(h->desc.n_docs, 256, h->num_sms), 256, 0, st>>>(b->d_doc_len, h->desc.n_docs, d_s);
+      ++h->launches;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sum_doc_len, d_s, sizeof(u64), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_s);
+    BM_CK(e);
+  }
+  return OI_OK;
+}
+
+extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *params) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OiBm25 *b = h->bm25;
+  if (!b) return h->fail(OI_ERR_STATE, "no BM25 index loaded");
+  if (!params || params->struct_size != sizeof(oi_bm25_params)) return h->fail(OI_ERR_INVALID_ARG, "bad oi_bm25_params (struct_size mismatch)");
+  if (!(params->k1 >= 0.0f) || !(params->b >= 0.0f && params->b <= 1.0f)) return h->fail(OI_ERR_INVALID_ARG, "k1 must be >= 0 and b in [0, 1]");
+  BM_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = h->stream;
+  // df: global if given, else this shard's list lengths
+  std::vector<uint32_t> df(b->n_terms);
+  if (params->global_df) {
+    std::copy(params->global_df, params->global_df + b->n_terms, df.begin());
+  } else {
+    std::vector<u64> off((size_t)b->n_terms + 1);
+    BM_CK(cudaMemcpyAsync(off.data(), b->d_term_off, off.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    BM_CK(cudaStreamSynchronize(st));
+    for (uint32_t t = 0; t < b->n_terms; ++t) df[t] = (uint32_t)(off[t + 1] - off[t]);
+  }
+  const uint64_t N = params->n_docs_global ? params->n_docs_global : h->desc.n_docs;
+  float avgdl = params->avgdl;
+  if (!(avgdl > 0.0f)) {
+    u64 *d_s = nullptr, sum = 0;
+    BM_CK(cudaMalloc(&d_s, sizeof(u64)));
+    cudaError_t e = cudaMemsetAsync(d_s, 0, sizeof(u64), st);
+    if (e == cudaSuccess && h->desc.n_docs) {
+      sum_u32_kernel<<<grid_for(h->desc.n_docs, 256, h->num_sms), 256, 0, st>>>(b->d_doc_len, h->desc.n_docs, d_s);
+      ++h->launches;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&sum, d_s, sizeof(u64), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_s);
+    BM_CK(e);
+    avgdl = h->desc.n_docs ? (float)((double)sum / (double)h->desc.n_docs) : 1.0f;
+  }
+  // idf: double on the host, rounded once (SPEC §3)
+  std::vector<float> idf(b->n_terms);
+  for (uint32_t t = 0; t < b->n_terms; ++t) {
+    const double d = (double)df[t];
+    idf[t] = df[t] == 0 ? 0.0f : (float)std::log(1.0 + ((double)N - d + 0.5) / (d + 0.5));
+  }
+  float *d_idf = nullptr;
+  BM_CK(cudaMalloc(&d_idf, (size_t)b->n_terms * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(d_idf, idf.data(), idf.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && b->n_postings) {
+    bm25_weights_kernel<<<grid_for(b->n_postings, 256, h->num_sms), 256, 0, st>>>(b->d_term_off, b->d_doc_ids, b->d_tfs, b->d_doc_len, d_idf,
+                                                                                  b->n_terms, b->n_postings, params->k1, params->b, avgdl, b->d_w);
+    ++h->launches;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_idf);
+  BM_CK(e);
+  b->finalized = true;
+  return OI_OK;
+}
+
+extern "C" oi_status oi_index_read_bm25(oi_index *h, uint64_t *term_offsets, uint32_t *doc_ids, uint32_t *tfs,
+                                        uint32_t *doc_len, float *weights) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OiBm25 *b = h->bm25;
+  if (!b) return h->fail(OI_ERR_STATE, "no BM25 index loaded");
+  if (weights && !b->finalized) return h->fail(OI_ERR_STATE, "weights requested before oi_index_bm25_finalize");
+  BM_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = h->stream;
+  const size_t P = b->n_postings;
+  if (term_offsets) BM_CK(cudaMemcpyAsync(term_offsets, b->d_term_off, ((size_t)b->n_terms + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  if (doc_ids && P) BM_CK(cudaMemcpyAsync(doc_ids, b->d_doc_ids, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (tfs && P) BM_CK(cudaMemcpyAsync(tfs, b->d_tfs, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (doc_len && h->desc.n_docs) BM_CK(cudaMemcpyAsync(doc_len, b->d_doc_len, h->desc.n_docs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (weights && P) BM_CK(cudaMemcpyAsync(weights, b->d_w, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BM_CK(cudaStreamSynchronize(st));
+  return OI_OK;
+}
+
+uint32_t oi_bm25_n_terms(const oi_index *h) { return h->bm25 ? h->bm25->n_terms : 0; }
+uint32_t *oi_bm25_stage_terms(oi_index *h) { return h->bm25 ? h->bm25->d_in_terms : nullptr; }
+uint32_t *oi_bm25_stage_offs(oi_index *h) { return h->bm25 ? h->bm25->d_in_offs : nullptr; }
+
+// Enqueues: prep -> blocked scoring -> per-query merge of the S lists into d_out_keys [nq][k]
+// (shard-local result, keys carry global doc ids).
+oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint32_t *d_q_offs, uint32_t nq,
+                             uint32_t k, u64 *d_out_keys, cudaStream_t st) {
+  OiBm25 *b = h->bm25;
+  if (!b || !b->finalized) return h->fail(OI_ERR_STATE, "BM25 index not loaded / not finalized");
+  if (nq == 0) return OI_OK;
+  bm25_prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_q_terms, d_q_offs, nq, b->d_term_off, b->n_terms,
+                                                             b->d_qterms, b->d_qnt, b->d_gthr, b->d_counter);
+  ++h->launches;
+  BM_CK(cudaGetLastError());
+
+  Bm25Params p;
+  p.term_off = b->d_term_off; p.doc_ids = b->d_doc_ids; p.w = b->d_w;
+  p.qterms = b->d_qterms; p.qnt = b->d_qnt; p.gthr = b->d_gthr; p.counter = b->d_counter; p.lists = b->d_lists;
+  p.n_docs = (uint32_t)h->desc.n_docs; p.doc_base = (uint32_t)h->desc.doc_base; p.nq = nq; p.k = k;
+  uint32_t cap = 256;
+  while (cap < 2 * k) cap <<= 1;
+  p.cap = cap;
+  // groups per CTA: as many as there are queries to spread (up to 16), bounded by 64 KB of candidates
+  uint32_t ng = 1;
+  while (ng < 16 && ng < nq) ng <<= 1;
+  while (ng > 1 && ng * cap > 8192) ng >>= 1;
+  if (h->bm25_variant >= 1 && h->bm25_variant <= 16) {  // tuning override: groups per CTA
+    uint32_t f = 1;
+    while (f * 2 <= (uint32_t)h->bm25_variant) f <<= 1;
+    if (f * cap <= 8192) ng = f;
+  }
+  p.group_size = OI_BM25_THREADS / ng;
+  p.R = OI_BM25_ACC_FLOATS / ng;
+  p.n_blocks = (p.n_docs + p.R - 1) / p.R;
+  if (p.n_blocks == 0) p.n_blocks = 1;
+  const uint32_t groups = (uint32_t)h->num_sms * ng;
+  uint32_t S = (3 * groups + nq - 1) / nq;
+  if (S < 1) S = 1;
+  if (S > p.n_blocks) S = p.n_blocks;
+  p.J = (p.n_blocks + S - 1) / S;
+  p.S = (p.n_blocks + p.J - 1) / p.J;
+  if ((size_t)p.S * nq > b->lists_cap) return h->fail(OI_ERR_CUDA, "internal: BM25 list workspace too small (%u x %u)", p.S, nq);
+  const size_t smem = sizeof(float) * OI_BM25_ACC_FLOATS + (size_t)ng * cap * sizeof(u64) +
+                      (size_t)ng * OI_BM25_MAX_QTERMS * (sizeof(u64) + 3 * sizeof(uint32_t)) + ng * sizeof(GrpCtl);
+  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  uint32_t grid = (uint32_t)h->num_sms;
+  const uint32_t ctas_useful = (p.S * nq + ng - 1) / ng;
+  if (grid > ctas_useful) grid = ctas_useful;
+  bm25_blocked_kernel<<<grid, OI_BM25_THREADS, smem, st>>>(p);
+  ++h->launches;
+  BM_CK(cudaGetLastError());
+  BM_CK(oi_launch_merge_shards(b->d_lists, p.S, nq, k, d_out_keys, st, &h->launches));
+  return OI_OK;
+}

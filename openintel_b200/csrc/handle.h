@@ -43,6 +43,11 @@ struct oi_index {
 
 // bm25.cu
 void oi_bm25_free(oi_index *h);
+uint32_t *oi_bm25_stage_terms(oi_index *h);  // device staging for the host call's flat term array
+uint32_t *oi_bm25_stage_offs(oi_index *h);
+// prep -> blocked scoring -> merge: shard-local sorted key lists d_out_keys[nq][k] (global doc ids)
+oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint32_t *d_q_offs, uint32_t nq,
+                             uint32_t k, u64 *d_out_keys, cudaStream_t st);
 // comm.cu
 void oi_comm_destroy(oi_index *h);
 // all-gathers each rank's [nq][k] local lists and merges them into d_out [nq][k] on every rank

@@ -52,6 +52,11 @@ cudaError_t oi_launch_unpack_keys(const u64 *d_keys, uint32_t n, uint32_t *d_ids
 cudaError_t oi_launch_merge_shards(const u64 *d_gathered, uint32_t world, uint32_t nq, uint32_t k,
                                    u64 *d_out, cudaStream_t stream, uint64_t *launches);
 
+// rrf.cu --------------------------------------------------------------------------------------
+cudaError_t oi_launch_rrf(const u64 *d_cos_keys, const u64 *d_bm25_keys, uint32_t nq, uint32_t k, uint32_t rrf_k,
+                          uint32_t *d_ids, float *d_rrf, uint32_t *d_rc, uint32_t *d_rb, cudaStream_t stream,
+                          uint64_t *launches);
+
 // synth.cu ------------------------------------------------------------------------------------
 cudaError_t oi_launch_synth_embeddings(void *d_mat, uint32_t dtype, uint64_t n_rows, uint32_t dim,
                                        uint64_t seed, uint64_t stream_id, uint64_t first_row,

@@ -1,0 +1,188 @@
+"""GPU parity: BM25 (index load / device synth / weights / blocked scoring + fused top-k), RRF and
+the hybrid call through the C ABI vs the CPU oracle.  SPEC §3/§4: bit-exact, no tie band."""
+import numpy as np
+import pytest
+
+import oracle as O
+from gpu_util import assert_ranked_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oi():
+    import __graft_entry__ as ge  # noqa: F401
+    import openintel_b200
+    openintel_b200.load_library()
+    return openintel_b200
+
+
+def _oracle_lists(corp, w, queries, n_docs, k, doc_base=0):
+    ids, scs = [], []
+    for q in queries:
+        sc = O.bm25_score_dense(corp["term_offsets"], corp["doc_ids"], w, np.asarray(q, dtype=np.uint32), n_docs)
+        i, s, _ = O.topk_f32(sc, k, only_positive=True, doc_base=doc_base)
+        ids.append(i)
+        scs.append(s)
+    return np.array(ids), np.array(scs)
+
+
+def _weights(corp, n_docs):
+    idf = O.bm25_idf(n_docs, np.diff(corp["term_offsets"]))
+    return O.bm25_weights(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"], idf)
+
+
+def test_device_synth_csr_is_bit_identical_to_oracle(oi):
+    n, vocab = 6000, 5000
+    corp = O.synth_bm25_corpus(n, vocab, first=250)
+    with oi.GpuIndex(n_docs=n, dim=64, doc_base=250) as ix:
+        ix.synth_bm25(O.SEED, vocab, corp["cdf"])
+        df, sdl, npost = ix.bm25_local_stats()
+        assert npost == len(corp["doc_ids"]) and sdl == int(corp["doc_len"].sum())
+        assert np.array_equal(df, np.diff(corp["term_offsets"]).astype(np.uint32))
+        ix.bm25_finalize()
+        got = ix.read_bm25(npost)
+    for name in ("term_offsets", "doc_ids", "tfs", "doc_len"):
+        assert np.array_equal(got[name], corp[name]), name
+    w = _weights(corp, n)
+    assert np.array_equal(got["weights"].view(np.uint32), w.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,vocab,k,nq,groups", [(20000, 3000, 100, 24, 0), (70000, 20000, 10, 5, 0), (5000, 300, 1, 3, 0),
+                                                 (40000, 1000, 100, 1, 0), (9000, 2000, 1000, 2, 0), (50000, 5000, 50, 40, 4),
+                                                 (50000, 5000, 50, 7, 1), (33000, 4000, 100, 16, 16)])
+def test_bm25_parity_bit_exact(oi, n, vocab, k, nq, groups):
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = _weights(corp, n)
+    qz = O.synth_query_terms(nq, 8, corp["cdf"])
+    qu = O.synth_query_terms(nq, 8, corp["cdf"], uniform=True)
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=nq, doc_base=11) as ix:
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.bm25_finalize()
+        if groups:
+            ix.set_option("bm25_variant", groups)
+        for qs in (qz, qu):
+            ids, sc = ix.search_bm25(qs, k)
+            wi, ws = _oracle_lists(corp, w, qs, n, k, doc_base=11)
+            assert np.array_equal(ids, wi)
+            assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
+
+
+def test_bm25_edge_cases(oi):
+    n, vocab, k = 12000, 1500, 20
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = _weights(corp, n)
+    queries = [
+        [],                                  # empty query: all padding
+        [vocab + 5, 4000000000],             # unknown terms only
+        [3, 3, 3, 3],                        # repeated term counts once
+        [0, 1, 2, vocab + 1, 2, 1],          # mixed
+        list(range(64)),                     # the maximum number of terms
+        [vocab - 1],                         # rarest term: list shorter than k?
+    ]
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=len(queries)) as ix:
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.bm25_finalize()
+        ids, sc = ix.search_bm25(queries, k)
+        wi, ws = _oracle_lists(corp, w, queries, n, k)
+        assert np.array_equal(ids, wi)
+        assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
+        assert np.all(ids[0] == oi.NO_DOC) and np.all(sc[0] == 0)
+        with pytest.raises(oi.OiError) as e:
+            ix.search_bm25([list(range(65))], k)
+        assert e.value.status == 1
+        # nq == 0 is a no-op
+        ids0, _ = ix.search_bm25([], k)
+        assert ids0.shape == (0, k)
+
+
+def test_bm25_before_finalize_is_a_state_error(oi):
+    corp = O.synth_bm25_corpus(500, 100)
+    with oi.GpuIndex(n_docs=500, dim=64, max_k=5) as ix:
+        with pytest.raises(oi.OiError) as e:
+            ix.search_bm25([[1, 2]], 5)
+        assert e.value.status == 5
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        with pytest.raises(oi.OiError) as e:
+            ix.search_bm25([[1, 2]], 5)
+        assert e.value.status == 5
+
+
+def test_bm25_global_statistics_make_shards_equal_the_whole(oi):
+    """SPEC §5: a sharded index scored with GLOBAL N / df / avgdl reproduces the unsharded lists."""
+    n, vocab, k, G = 30000, 4000, 50, 3
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = _weights(corp, n)
+    qs = O.synth_query_terms(6, 8, corp["cdf"])
+    want_ids, want_sc = _oracle_lists(corp, w, qs, n, k)
+    gdf = np.diff(corp["term_offsets"]).astype(np.uint32)
+    avgdl = O.bm25_avgdl(corp["doc_len"])
+    per = (n + G - 1) // G
+    all_ids, all_sc = [], []
+    for r in range(G):
+        lo, hi = r * per, min(n, (r + 1) * per)
+        with oi.GpuIndex(n_docs=hi - lo, dim=64, max_k=k, max_batch=6, doc_base=lo) as ix:
+            ix.synth_bm25(O.SEED, vocab, corp["cdf"])
+            ix.bm25_finalize(avgdl=avgdl, n_docs_global=n, global_df=gdf)
+            ids, sc = ix.search_bm25(qs, k)
+        all_ids.append(ids)
+        all_sc.append(sc)
+    for j in range(6):
+        cand = [(O.key(float(s), int(d)), int(d), s) for r in range(G) for d, s in zip(all_ids[r][j], all_sc[r][j]) if d != oi.NO_DOC]
+        cand.sort(key=lambda t: -t[0])
+        got = [c[1] for c in cand[:k]]
+        assert got == [int(x) for x in want_ids[j] if x != oi.NO_DOC]
+        assert [c[2].view(np.uint32) for c in cand[:k]] == [s.view(np.uint32) for s, d in zip(want_sc[j], want_ids[j]) if d != oi.NO_DOC]
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_hybrid_matches_oracle(oi, k):
+    n, dim, vocab, nq = 30000, 384, 3000, 6
+    rows = O.synth_rows_f32(n, dim)
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = _weights(corp, n)
+    qv = np.concatenate([O.synth_rows_f32(3, dim, stream=1), O.synth_planted_queries(3, dim, n)[0]])
+    qt = O.synth_query_terms(nq, 8, corp["cdf"])
+    with oi.GpuIndex(n_docs=n, dim=dim, max_k=k, max_batch=nq) as ix:
+        ix.synth_embeddings(O.SEED)
+        ix.synth_bm25(O.SEED, vocab, corp["cdf"])
+        ix.bm25_finalize()
+        cos_ids, cos_sc = ix.search_cosine(qv, k)
+        bm_ids, bm_sc = ix.search_bm25(qt, k)
+        ids, rrf, rc, rb = ix.search_hybrid(qv, qt, k)
+    wb_ids, wb_sc = _oracle_lists(corp, w, qt, n, k)
+    assert np.array_equal(bm_ids, wb_ids)
+    for j in range(nq):
+        allsc = O.cosine_scores_f32(rows, qv[j])
+        wi, ws, _ = O.topk_f64(allsc, k)
+        swaps = assert_ranked_close(cos_ids[j], cos_sc[j], wi, ws, allsc, 1e-5)
+        # RRF is bit-exact GIVEN the two input lists (SPEC §4): fuse the GPU's own lists with the oracle
+        oi_ids, oi_val, oi_rc, oi_rb, m = O.rrf(cos_ids[j], bm_ids[j], k)
+        assert np.array_equal(ids[j], oi_ids)
+        assert np.array_equal(rrf[j].view(np.uint32), oi_val.view(np.uint32))
+        assert np.array_equal(rc[j], oi_rc) and np.array_equal(rb[j], oi_rb)
+        if swaps == 0:  # and end to end when the cosine list had no tie-band swap
+            e_ids, e_val, _, _, _ = O.rrf(wi, wb_ids[j], k)
+            assert np.array_equal(ids[j], e_ids) and np.array_equal(rrf[j].view(np.uint32), e_val.view(np.uint32))
+
+
+def test_rrf_short_and_disjoint_lists(oi):
+    """BM25 list shorter than k (padding) and a query with no lexical match at all."""
+    n, dim, vocab, k = 4000, 128, 50000, 30
+    corp = O.synth_bm25_corpus(n, vocab)
+    qv = O.synth_rows_f32(2, dim, stream=1)
+    rare = int(np.nonzero(np.diff(corp["term_offsets"]) == 1)[0][0])
+    qt = [[rare], [vocab + 9]]
+    with oi.GpuIndex(n_docs=n, dim=dim, max_k=k, max_batch=2) as ix:
+        ix.synth_embeddings(O.SEED)
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.bm25_finalize()
+        cos_ids, _ = ix.search_cosine(qv, k)
+        bm_ids, _ = ix.search_bm25(qt, k)
+        ids, rrf, rc, rb = ix.search_hybrid(qv, qt, k)
+    assert (bm_ids[0] != oi.NO_DOC).sum() == 1 and np.all(bm_ids[1] == oi.NO_DOC)
+    for j in range(2):
+        e_ids, e_val, e_rc, e_rb, _ = O.rrf(cos_ids[j], bm_ids[j], k)
+        assert np.array_equal(ids[j], e_ids) and np.array_equal(rrf[j].view(np.uint32), e_val.view(np.uint32))
+        assert np.array_equal(rc[j], e_rc) and np.array_equal(rb[j], e_rb)
+    assert np.all(rb[1] == 0)

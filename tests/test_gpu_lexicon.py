@@ -1,0 +1,76 @@
+"""GPU parity: the batched lexicon scorer (GPU PostAnalyzer) vs the reference's goldens and the
+oracle's restatement of src/adapters/analyzer/lexicon.rs:53-73.  Integer hit counts and the f64
+polarity are compared exactly."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oi():
+    import __graft_entry__ as ge  # noqa: F401
+    import openintel_b200
+    openintel_b200.load_library()
+    return openintel_b200
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    with open(os.path.join(golden_dir, "reference_lexicon_goldens.json"), encoding="utf-8") as f:
+        return json.load(f)
+
+
+def _check(oi, texts):
+    pol, spec, bull, bear = oi.lexicon_analyze(texts)
+    for i, t in enumerate(texts):
+        wp, ws, wb, we = O.lexicon_score(t)
+        assert (pol[i], bool(spec[i]), int(bull[i]), int(bear[i])) == (wp, ws, wb, we), repr(t)
+    return pol, spec
+
+
+def test_reference_goldens(oi, G):
+    cases = G["lexicon_unit"]["cases"]
+    pol, spec = _check(oi, [c["text"] for c in cases])
+    for i, c in enumerate(cases):
+        assert int(pol[i] > 0) - int(pol[i] < 0) == c["polarity_sign"] and bool(spec[i]) == c["speculative"]
+    posts = G["fixture_posts"]["posts"]
+    pol, spec = _check(oi, [p["text"] for p in posts])
+    assert [float(x) for x in pol] == [p["polarity"] for p in posts]
+    assert [bool(x) for x in spec] == [p["speculative"] for p in posts]
+    s = O.social_summary(pol, spec.astype(np.int32))
+    d = G["fixture_posts"]["summary"]["derived"]
+    assert (s["net_sentiment"], s["speculation_index"], s["bullish"], s["bearish"]) == \
+        (d["net_sentiment"], d["speculation_index"], d["bullish"], d["bearish"])
+
+
+def test_tokenizer_edge_cases_and_random_text(oi, G):
+    texts = [c["text"] for c in G["tokenizer_rules"]["cases"]]
+    texts += ["", " ", "moon", "MOON", "moon moon dump", "$CALLS!", "0dte", "0DTE.", "xmoon", "moonx", "mo on",
+              "Kalls calls", "pumpİt", "rİp", "İv iv", "buK", "long" * 3000, "a" * 10000,
+              "up " * 3333, "é" * 500 + "bear", "🚀rocket🚀", "iv̇", "bagholder contracts", "contractsx"]
+    rnd = random.Random(11)
+    alphabet = list("abcXYZ019 $_-.,!\n\t") + ["é", "İ", "K", "ß", "Σ", "日", "🚀", "̇"]
+    words = ["moon", "calls", "puts", "yolo", "Dump", "RIP", "iv", "red", "GREEN", "strike", "bear", "up"]
+    for _ in range(400):
+        parts = [rnd.choice(words) if rnd.random() < 0.4 else "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 12)))
+                 for _ in range(rnd.randint(0, 30))]
+        texts.append(rnd.choice([" ", "", ",", "K", "İ"]).join(parts))
+    _check(oi, texts)
+
+
+def test_large_batch_is_aligned_to_input_order(oi):
+    rnd = random.Random(5)
+    words = ["moon", "calls", "puts", "sell", "the", "stock", "0dte", "report", "up", "down", "x"]
+    texts = [" ".join(rnd.choice(words) for _ in range(rnd.randint(1, 60))) for _ in range(20000)]
+    pol, spec, bull, bear = oi.lexicon_analyze(texts)
+    assert len(pol) == len(texts)
+    for i in range(0, len(texts), 37):
+        wp, ws, wb, we = O.lexicon_score(texts[i])
+        assert (pol[i], bool(spec[i]), int(bull[i]), int(bear[i])) == (wp, ws, wb, we)
