@@ -97,6 +97,8 @@ extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) 
   if ((e = cudaMalloc(&h->cws.ticket, B * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(ticket)", e);
   if ((e = cudaMemset(h->cws.gthr, 0, B * sizeof(u64))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMemset(h->cws.ticket, 0, B * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMalloc(&h->cws.tile_ctr, B * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(tile_ctr)", e);
+  if ((e = cudaMemset(h->cws.tile_ctr, 0, B * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&h->d_queries, B * desc->dim * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(queries)", e);
   if ((e = cudaMalloc(&h->d_keys_cos, B * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
   if ((e = cudaMalloc(&h->d_keys_bm25, B * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
@@ -116,6 +118,7 @@ extern "C" void oi_index_destroy(oi_index *h) {
   cudaFree(h->cws.cand);
   cudaFree(h->cws.gthr);
   cudaFree(h->cws.ticket);
+  cudaFree(h->cws.tile_ctr);
   cudaFree(h->d_queries);
   cudaFree(h->d_keys_cos);
   cudaFree(h->d_keys_bm25);

@@ -138,10 +138,12 @@ struct Bm25Params {
 
 // One warp applies its share of term postings [pos, e) that fall below doc id `bend`.
 // Chunks of 128 postings are dealt round-robin to the `n_warps` warps of the group (warp `wg`
-// takes chunks wg, wg + n_warps, ...).  Returns the number of in-block postings this warp applied.
+// takes chunks wg, wg + n_warps, ...).  Returns the number of in-block postings this warp applied;
+// *first_out = the doc id of the first posting this warp saw that is NOT in the block
+// (0xFFFFFFFF when its share of the list is exhausted).
 __device__ __forceinline__ uint32_t walk_term(const uint32_t *__restrict__ dids, const float *__restrict__ ws,
                                               uint32_t pos, uint32_t e, uint32_t bbase, uint32_t bend,
-                                              float *acc, int wg, int n_warps, int lane) {
+                                              float *acc, int wg, int n_warps, int lane, uint32_t *first_out) {
   uint32_t total = 0;
   uint32_t c = pos + (uint32_t)wg * OI_BM25_CHUNK;
   uint32_t d[4];
@@ -149,7 +151,7 @@ __device__ __forceinline__ uint32_t walk_term(const uint32_t *__restrict__ dids,
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint32_t p = c + 32 * j + lane;
-    const bool ok = p < e && p >= c;  // p >= c guards u32 wrap
+    const bool ok = p < e;
     d[j] = ok ? __ldg(dids + p) : 0xFFFFFFFFu;
     w[j] = ok ? __ldg(ws + p) : 0.0f;
   }
@@ -163,7 +165,7 @@ __device__ __forceinline__ uint32_t walk_term(const uint32_t *__restrict__ dids,
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // prefetch this warp's next chunk before touching shared memory
         const uint32_t p = cn + 32 * j + lane;
-        const bool ok = p < e && p >= cn;
+        const bool ok = p < e;
         d2[j] = ok ? __ldg(dids + p) : 0xFFFFFFFFu;
         w2[j] = ok ? __ldg(ws + p) : 0.0f;
       }
@@ -188,6 +190,10 @@ __device__ __forceinline__ uint32_t walk_term(const uint32_t *__restrict__ dids,
         n += __popc(__ballot_sync(0xFFFFFFFFu, in));
       }
       total += n;
+      // n < 128 here: posting n of the chunk is the first one outside the block
+      const uint32_t jn = n >> 5;
+      const uint32_t dj = jn == 0 ? d[0] : jn == 1 ? d[1] : jn == 2 ? d[2] : d[3];
+      *first_out = __shfl_sync(0xFFFFFFFFu, dj, n & 31);
       break;
     }
   }
@@ -201,6 +207,7 @@ __device__ __forceinline__ uint32_t walk_term(const uint32_t *__restrict__ dids,
 //   u32   tcur[NG][64]       cursor inside the list (postings consumed so far)
 //   u32   tend[NG][64]       list length
 //   u32   tnxt[NG][64]       doc id at the cursor (0xFFFFFFFF = exhausted)
+//   u32   tnew[NG][64]       min-reduction slot for the next value of tnxt
 //   GrpCtl ctl[NG]
 __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const Bm25Params p) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -220,7 +227,8 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
   uint32_t *tcur_all = reinterpret_cast<uint32_t *>(tbase_all + (size_t)NG * OI_BM25_MAX_QTERMS);
   uint32_t *tend_all = tcur_all + NG * OI_BM25_MAX_QTERMS;
   uint32_t *tnxt_all = tend_all + NG * OI_BM25_MAX_QTERMS;
-  GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(tnxt_all + NG * OI_BM25_MAX_QTERMS);
+  uint32_t *tnew_all = tnxt_all + NG * OI_BM25_MAX_QTERMS;
+  GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(tnew_all + NG * OI_BM25_MAX_QTERMS);
 
   const uint32_t R = p.R;
   float *acc = acc_all + (size_t)gi * R;
@@ -229,6 +237,7 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
   uint32_t *tcur = tcur_all + gi * OI_BM25_MAX_QTERMS;
   uint32_t *tend = tend_all + gi * OI_BM25_MAX_QTERMS;
   uint32_t *tnxt = tnxt_all + gi * OI_BM25_MAX_QTERMS;
+  uint32_t *tnew = tnew_all + gi * OI_BM25_MAX_QTERMS;
   GrpCtl *ctl = ctl_all + gi;
 
   for (uint32_t i = g.tid; i < R; i += GS) acc[i] = 0.0f;
@@ -259,64 +268,101 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
       tcur[i] = (uint32_t)(a - lo);
       tend[i] = (uint32_t)(hi - lo);
       tnxt[i] = a < hi ? __ldg(p.doc_ids + a) : 0xFFFFFFFFu;
+      tnew[i] = 0xFFFFFFFFu;
     }
     if (g.tid == 0) { ctl->cnt = 0; ctl->thr = 0ull; ctl->aux = 0; }
     g.sync();
 
-    for (uint32_t blk = blk0; blk < blk1; ++blk) {
+    uint32_t blk = blk0;
+    while (blk < blk1) {
+      // ---- skip straight to the next block that holds a posting of any query term -------------
+      uint32_t mn = 0xFFFFFFFFu;
+      for (uint32_t i = 0; i < nt; ++i) mn = min(mn, tnxt[i]);  // group-uniform (shared memory)
+      if (mn == 0xFFFFFFFFu) break;
+      blk = max(blk, mn / R);
+      if (blk >= blk1) break;
       const uint32_t bbase = blk * R;
       const uint32_t bend = min(p.n_docs, bbase + R);
-      // ---- term passes, ascending term id -------------------------------------------------------
-      bool touched = false;
-      for (uint32_t i = 0; i < nt; ++i) {
-        if (tnxt[i] >= bend) continue;  // group-uniform: this list has nothing in the block
-        touched = true;
-        const uint32_t pos = tcur[i], e = tend[i];
-        const u64 base = tbase[i];
-        const uint32_t n = walk_term(p.doc_ids + base, p.w + base, pos, e, bbase, bend, acc, wg, n_warps, lane);
-        g.sync();  // every read of tcur[i] and every add of this pass is done
-        if (lane == 0 && n) atomicAdd(&tcur[i], n);
+      ++blk;
+      // ---- term passes, ascending term id; the first 32-posting slice of up to 8 lists is
+      //      fetched up front so that one memory latency covers all of them ----------------------
+      for (uint32_t i0 = 0; i0 < nt; i0 += 8) {
+        uint32_t pd[8];
+        float pw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t i = i0 + u;
+          pd[u] = 0xFFFFFFFFu;
+          pw[u] = 0.0f;
+          if (i < nt && tnxt[i] < bend) {
+            const uint32_t pp = tcur[i] + (uint32_t)wg * 32 + lane;
+            if (pp < tend[i]) {
+              pd[u] = __ldg(p.doc_ids + tbase[i] + pp);
+              pw[u] = __ldg(p.w + tbase[i] + pp);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t i = i0 + u;
+          if (i >= nt || tnxt[i] >= bend) continue;  // group-uniform: this list has nothing in the block
+          uint32_t n, fo;
+          const bool full0 = __shfl_sync(0xFFFFFFFFu, pd[u], 31) < bend;
+          if (!full0) {
+            const bool in = pd[u] < bend;
+            if (in) {
+              float *a = acc + (pd[u] - bbase);
+              *a = *a + pw[u];
+            }
+            n = __popc(__ballot_sync(0xFFFFFFFFu, in));  // <= 31
+            fo = __shfl_sync(0xFFFFFFFFu, pd[u], n);
+          } else {
+            float *a = acc + (pd[u] - bbase);
+            *a = *a + pw[u];
+            const u64 base = tbase[i];
+            n = 32 + walk_term(p.doc_ids + base, p.w + base, tcur[i] + (uint32_t)n_warps * 32, tend[i], bbase, bend,
+                               acc, wg, n_warps, lane, &fo);
+          }
+          g.sync();  // every read of tcur[i] / tnxt[i] and every add of this pass is done
+          if (lane == 0) {
+            if (n) atomicAdd(&tcur[i], n);
+            atomicMin(&tnew[i], fo);
+          }
+        }
       }
-      if (!touched) continue;  // acc[] is still all zero
       g.sync();
       for (uint32_t i = g.tid; i < nt; i += GS) {
-        const uint32_t c = tcur[i];
-        if (tnxt[i] < bend) tnxt[i] = c < tend[i] ? __ldg(p.doc_ids + tbase[i] + c) : 0xFFFFFFFFu;
+        if (tnxt[i] < bend) { tnxt[i] = tnew[i]; tnew[i] = 0xFFFFFFFFu; }
       }
       // ---- selection: positive scores that beat the running threshold -------------------------
       const u64 thr = max(ctl->thr, ld_relaxed_u64(p.gthr + q));
-      const uint32_t span_all = bend - bbase;
+      const float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
       const uint32_t cnt0 = ctl->cnt;
+      const float4 *acc4 = reinterpret_cast<const float4 *>(acc);
       g.sync();
-      // optimistic pass: count first; in steady state only a handful survive
-      uint32_t mine = 0;
-      for (uint32_t j = g.tid; j < span_all; j += GS) {
-        const float sc = acc[j];
-        if (sc > 0.0f && oi_make_key(sc, p.doc_base + bbase + j) > thr) ++mine;
-      }
-      mine = __reduce_add_sync(0xFFFFFFFFu, mine);
-      if (lane == 0 && mine) atomicAdd(&ctl->aux, mine);
-      g.sync();
-      const uint32_t survivors = ctl->aux;
-      g.sync();
-      if (g.tid == 0) ctl->aux = 0;
-      if (survivors <= cap - cnt0) {
-        if (survivors) {
-          for (uint32_t j = g.tid; j < span_all; j += GS) {
-            const float sc = acc[j];
-            if (sc > 0.0f) {
-              const u64 key = oi_make_key(sc, p.doc_base + bbase + j);
+      // optimistic pass: push with a bounds check; in steady state only a handful survive
+      for (uint32_t j = g.tid; j < R / 4; j += GS) {
+        const float4 v = acc4[j];
+        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (m4 > 0.0f && m4 >= tsc) {
+          const float sc4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            if (sc4[c4] > 0.0f && sc4[c4] >= tsc) {
+              const u64 key = oi_make_key(sc4[c4], p.doc_base + bbase + 4 * j + c4);
               if (key > thr) { const uint32_t at = atomicAdd(&ctl->cnt, 1u); if (at < cap) cand[at] = key; }
             }
           }
         }
+      }
+      g.sync();
+      if (ctl->cnt > cap) {
+        // overflow (cold threshold): drop this block's pushes and redo it in spans that cannot
+        // overflow the buffer, compacting between spans
         g.sync();
-        if (ctl->cnt > cap / 2) {
-          grp_compact(cand, ctl, cap, k, g);
-          if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
-        }
-      } else {
-        // slow path (cold threshold): spans that cannot overflow the buffer, compacting between
+        if (g.tid == 0) ctl->cnt = cnt0;
+        g.sync();
+        const uint32_t span_all = bend - bbase;
         uint32_t b0 = 0;
         while (b0 < span_all) {
           const uint32_t span = min(span_all - b0, cap - ctl->cnt);
@@ -336,8 +382,12 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
             if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
           }
         }
+      } else if (ctl->cnt > cap / 2) {
+        grp_compact(cand, ctl, cap, k, g);
+        if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
       }
-      for (uint32_t j = g.tid; j < span_all; j += GS) acc[j] = 0.0f;
+      float4 *accw = reinterpret_cast<float4 *>(acc);
+      for (uint32_t j = g.tid; j < R / 4; j += GS) accw[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       g.sync();
     }
     // ---- item done: publish the sorted list ---------------------------------------------------
@@ -806,7 +856,7 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   p.S = (p.n_blocks + p.J - 1) / p.J;
   if ((size_t)p.S * nq > b->lists_cap) return h->fail(OI_ERR_CUDA, "internal: BM25 list workspace too small (%u x %u)", p.S, nq);
   const size_t smem = sizeof(float) * OI_BM25_ACC_FLOATS + (size_t)ng * cap * sizeof(u64) +
-                      (size_t)ng * OI_BM25_MAX_QTERMS * (sizeof(u64) + 3 * sizeof(uint32_t)) + ng * sizeof(GrpCtl);
+                      (size_t)ng * OI_BM25_MAX_QTERMS * (sizeof(u64) + 4 * sizeof(uint32_t)) + ng * sizeof(GrpCtl);
   BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   uint32_t grid = (uint32_t)h->num_sms;
   const uint32_t ctas_useful = (p.S * nq + ng - 1) / ng;

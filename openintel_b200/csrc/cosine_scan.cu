@@ -133,7 +133,7 @@ __device__ void scan_epilogue(SelState &S, const OiScanParams &p, int tid, int n
   }
   // (3) emit and re-arm the per-query control words for the next launch
   for (uint32_t i = tid; i < k; i += nthreads) p.out_keys[i] = i < S.cnt ? S.buf[i] : 0ull;
-  if (tid == 0) { *p.ticket = 0; *p.gthr = 0ull; }
+  if (tid == 0) { *p.ticket = 0; *p.tile_ctr = 0; *p.gthr = 0ull; }
 }
 
 // =================================================================================================
@@ -256,11 +256,21 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_generic_kerne
 }
 
 // =================================================================================================
-// Variant 1: bulk-async-copy pipeline.  Warp 8 is the producer; warps 0-7 consume.
-// Dynamic smem: [n_stages][tile_bytes] row tiles (128 B aligned) then 2*n_stages mbarriers.
+// Variant 1 (default): bulk-async-copy pipeline with dynamic tiles.  One CTA per SM.  Warp 8 is
+// the producer: it draws row tiles from a grid-wide atomic counter (one ticket ahead, so the
+// round trip to L2 is off the critical path) and streams them with cp.async.bulk (TMA 1-D, SASS
+// UBLKCP) through an mbarrier ring; warps 0-7 reduce rows from shared memory.  Dynamic tiles make
+// every SM finish within one tile of the others (no tail), and the copy engine keeps
+// n_stages x tile_bytes (~190 KB) in flight per SM without spending registers on it.
+// Dynamic smem: [n_stages][tile_bytes] row tiles (128 B aligned), 2*n_stages mbarriers, then
+// n_stages u32 tile ids.
 // =================================================================================================
-template <typename T, int NVL>
-__global__ void __launch_bounds__(kConsumerThreads + 32, 1)
+constexpr uint32_t kTileEnd = 0xFFFFFFFFu;
+constexpr int kBulkWarps = 16;                  // consumer warps of the bulk variant
+constexpr int kBulkThreads = kBulkWarps * 32;   // + one producer warp
+
+template <typename T, int NVL, bool EXACT>
+__global__ void __launch_bounds__(kBulkThreads + 32, 1)
     cosine_scan_bulk_kernel(const OiScanParams p, const uint32_t tile_rows, const uint32_t n_stages) {
   constexpr int QF = Elem<T>::QF;
   extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -270,95 +280,135 @@ __global__ void __launch_bounds__(kConsumerThreads + 32, 1)
   const uint32_t tile_bytes = tile_rows * row_bytes;
   u64 *full = reinterpret_cast<u64 *>(s_dyn + (size_t)n_stages * tile_bytes);
   u64 *empty = full + n_stages;
-
-  const uint32_t row_begin = min(p.n_rows, blockIdx.x * p.rows_per_cta);
-  const uint32_t row_end = min(p.n_rows, row_begin + p.rows_per_cta);
-  const uint32_t n_tiles = (row_end - row_begin + tile_rows - 1) / tile_rows;
+  uint32_t *s_tile = reinterpret_cast<uint32_t *>(empty + n_stages);
+  const uint32_t n_tiles = (p.n_rows + tile_rows - 1) / tile_rows;
 
   if (tid == 0) {
-    for (uint32_t s = 0; s < n_stages; ++s) { oi_mbar_init(&full[s], 1); oi_mbar_init(&empty[s], kConsumerWarps); }
+    for (uint32_t s = 0; s < n_stages; ++s) { oi_mbar_init(&full[s], 1); oi_mbar_init(&empty[s], kBulkWarps); }
     oi_mbar_fence_init();
     S.cnt = 0; S.thr = 0ull;
   }
   __syncthreads();
 
-  if (warp == kConsumerWarps) {
-    // ---------------- producer: one elected lane streams the CTA's row range -----------------
+  if (warp == kBulkWarps) {
+    // ---------------- producer: one elected lane, all queries of the batch back to back ----------
     if (lane == 0) {
       const u64 policy = oi_policy_evict_first();
-      const unsigned char *src = reinterpret_cast<const unsigned char *>(p.mat) + (size_t)row_begin * row_bytes;
-      for (uint32_t t = 0; t < n_tiles; ++t) {
-        const uint32_t s = t % n_stages, ph = (t / n_stages) & 1u;
-        oi_mbar_wait(&empty[s], ph ^ 1u);
-        const uint32_t rows = min(tile_rows, row_end - row_begin - t * tile_rows);
-        const uint32_t bytes = rows * row_bytes;
-        oi_mbar_expect_tx(&full[s], bytes);
-        oi_bulk_g2s(s_dyn + (size_t)s * tile_bytes, src + (size_t)t * tile_bytes, bytes, &full[s], policy);
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(p.mat);
+      uint32_t it = 0;
+      for (uint32_t qi = 0; qi < p.nq; ++qi) {
+        uint32_t *ctr = p.tile_ctr + qi;
+        uint32_t t = atomicAdd(ctr, 1u);
+        for (;; ++it) {
+          const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+          const uint32_t t_next = t < n_tiles ? atomicAdd(ctr, 1u) : kTileEnd;  // ticket for the next round
+          oi_mbar_wait(&empty[s], ph ^ 1u);
+          if (t >= n_tiles) {
+            s_tile[s] = kTileEnd;  // end of this query: the consumers run its epilogue
+            oi_mbar_arrive(&full[s]);
+            ++it;
+            break;
+          }
+          s_tile[s] = t;
+          const uint32_t rows = min(tile_rows, p.n_rows - t * tile_rows);
+          const uint32_t bytes = rows * row_bytes;
+          oi_mbar_expect_tx(&full[s], bytes);
+          oi_bulk_g2s(s_dyn + (size_t)s * tile_bytes, src + (size_t)t * tile_bytes, bytes, &full[s], policy);
+          t = t_next;
+        }
       }
     }
-    return;  // the producer warp takes no part in barrier 1 or the epilogue
+    return;  // the producer warp takes no part in barrier 1 or the epilogues
   }
 
   // -------------------------------- consumers --------------------------------------------------
-  float q[NVL][QF];
+  uint32_t it = 0;
+  for (uint32_t qi = 0; qi < p.nq; ++qi) {
+    OiScanParams pq = p;
+    pq.q = p.q + (size_t)qi * p.dim;
+    pq.cand = p.cand + (size_t)qi * p.cand_stride;
+    pq.gthr = p.gthr + qi;
+    pq.ticket = p.ticket + qi;
+    pq.tile_ctr = p.tile_ctr + qi;
+    pq.out_keys = p.out_keys + (size_t)qi * p.k;
+    float q[NVL][QF];
 #pragma unroll
-  for (int j = 0; j < NVL; ++j) {
-    const uint32_t v = lane + 32 * j;
-    if (v < p.nv) {
-      Elem<T>::load_q(p.q, v, q[j]);
-    } else {
+    for (int j = 0; j < NVL; ++j) {
+      const uint32_t v = lane + 32 * j;
+      if (EXACT || v < p.nv) {
+        Elem<T>::load_q(pq.q, v, q[j]);
+      } else {
 #pragma unroll
-      for (int e = 0; e < QF; ++e) q[j][e] = 0.0f;
-    }
-  }
-
-  uint32_t t = 0;
-  while (t < n_tiles) {
-    // super-iteration over as many tiles as the candidate buffer can absorb in the worst case
-    const uint32_t tiles_now = min(n_tiles - t, max(1u, ((uint32_t)OI_SEL_CAP - S.cnt) / tile_rows));
-    const u64 thr = max(S.thr, ld_relaxed_u64(p.gthr));
-    oi_bar_sync(1, kConsumerThreads);  // (cnt, thr) snapshot is uniform before anybody pushes
-    for (uint32_t tt = t; tt < t + tiles_now; ++tt) {
-      const uint32_t s = tt % n_stages, ph = (tt / n_stages) & 1u;
-      const uint32_t tile_row0 = row_begin + tt * tile_rows;
-      const uint32_t rows = min(tile_rows, row_end - tile_row0);
-      oi_mbar_wait(&full[s], ph);
-      const unsigned char *tile = s_dyn + (size_t)s * tile_bytes;
-      for (uint32_t r = warp * 2; r < rows; r += kConsumerWarps * 2) {
-        const uint4 *rp0 = reinterpret_cast<const uint4 *>(tile + (size_t)r * row_bytes);
-        const bool two = r + 1 < rows;
-        const uint4 *rp1 = reinterpret_cast<const uint4 *>(tile + (size_t)(r + (two ? 1 : 0)) * row_bytes);
-        float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NVL; ++j) {
-          const uint32_t v = lane + 32 * j;
-          if (v < p.nv) {
-            a0 = Elem<T>::dot(rp0[v], q[j], a0);
-            a1 = Elem<T>::dot(rp1[v], q[j], a1);
-          }
-        }
-        a0 = warp_sum(a0);
-        a1 = warp_sum(a1);
-        if (lane == 0) {
-          u64 k0 = oi_make_key(a0, p.doc_base + tile_row0 + r);
-          if (k0 > thr) oi_sel_push(S.buf, &S.cnt, k0);
-          if (two) {
-            u64 k1 = oi_make_key(a1, p.doc_base + tile_row0 + r + 1);
-            if (k1 > thr) oi_sel_push(S.buf, &S.cnt, k1);
-          }
-        }
+        for (int e = 0; e < QF; ++e) q[j][e] = 0.0f;
       }
-      __syncwarp();
-      if (lane == 0) oi_mbar_arrive(&empty[s]);
     }
-    t += tiles_now;
-    oi_bar_sync(1, kConsumerThreads);
-    if (t < n_tiles && S.cnt > OI_SEL_CAP / 2) {
-      oi_sel_compact(S.buf, &S.cnt, &S.thr, p.k, tid, kConsumerThreads, 1);
-      if (tid == 0 && S.cnt == p.k) atomicMax(p.gthr, S.thr);
+    bool done = false;
+    while (!done) {
+      // super-iteration over as many tiles as the candidate buffer can absorb in the worst case
+      const uint32_t tiles_now = max(1u, ((uint32_t)OI_SEL_CAP - S.cnt) / tile_rows);
+      const u64 thr = max(S.thr, ld_relaxed_u64(pq.gthr));
+      oi_bar_sync(1, kBulkThreads);  // (cnt, thr) snapshot is uniform before anybody pushes
+      for (uint32_t n = 0; n < tiles_now; ++n) {
+        const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+        oi_mbar_wait(&full[s], ph);
+        const uint32_t t = s_tile[s];
+        ++it;
+        if (t == kTileEnd) {  // every consumer warp sees the same sentinel; the slot holds no data
+          __syncwarp();
+          if (lane == 0) oi_mbar_arrive(&empty[s]);
+          done = true;
+          break;
+        }
+        const uint32_t tile_row0 = t * tile_rows;
+        const uint32_t rows = min(tile_rows, p.n_rows - tile_row0);
+        const unsigned char *tile = s_dyn + (size_t)s * tile_bytes;
+        for (uint32_t r = warp * 2; r < rows; r += kBulkWarps * 2) {
+          const uint4 *rp0 = reinterpret_cast<const uint4 *>(tile + (size_t)r * row_bytes);
+          const bool two = r + 1 < rows;
+          const uint4 *rp1 = two ? reinterpret_cast<const uint4 *>(tile + (size_t)(r + 1) * row_bytes) : rp0;
+          float a0[NVL], a1[NVL];
+#pragma unroll
+          for (int j = 0; j < NVL; ++j) {
+            const uint32_t v = lane + 32 * j;
+            a0[j] = 0.0f; a1[j] = 0.0f;
+            if (EXACT || v < p.nv) {
+              a0[j] = Elem<T>::dot(rp0[v], q[j], 0.0f);
+              a1[j] = Elem<T>::dot(rp1[v], q[j], 0.0f);
+            }
+          }
+          float s0 = a0[0], s1 = a1[0];
+#pragma unroll
+          for (int j = 1; j < NVL; ++j) { s0 += a0[j]; s1 += a1[j]; }
+          // two rows share one butterfly: after the first exchange lanes 0-15 carry row r,
+          // lanes 16-31 row r+1
+          const bool hi = lane & 16;
+          float keep = hi ? s1 : s0;
+          keep += __shfl_xor_sync(0xFFFFFFFFu, hi ? s0 : s1, 16);
+          keep += __shfl_xor_sync(0xFFFFFFFFu, keep, 8);
+          keep += __shfl_xor_sync(0xFFFFFFFFu, keep, 4);
+          keep += __shfl_xor_sync(0xFFFFFFFFu, keep, 2);
+          keep += __shfl_xor_sync(0xFFFFFFFFu, keep, 1);
+          if ((lane & 15) == 0 && (!hi || two)) {
+            const u64 key = oi_make_key(keep, p.doc_base + tile_row0 + r + (hi ? 1u : 0u));
+            if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) oi_mbar_arrive(&empty[s]);
+      }
+      oi_bar_sync(1, kBulkThreads);
+      if (!done && S.cnt > OI_SEL_CAP / 2) {
+        oi_sel_compact(S.buf, &S.cnt, &S.thr, p.k, tid, kBulkThreads, 1);
+        if (tid == 0 && S.cnt == p.k) atomicMax(pq.gthr, S.thr);
+      }
     }
+    // this query is done in this CTA: publish its list (the last CTA to arrive merges) while the
+    // producer already streams the next query's tiles into the ring
+    scan_epilogue(S, pq, tid, kBulkThreads, 1);
+    oi_bar_sync(1, kBulkThreads);
+    if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
+    oi_bar_sync(1, kBulkThreads);
   }
-  scan_epilogue(S, p, tid, kConsumerThreads, 1);
 }
 
 // ---- host-side dispatch -------------------------------------------------------------------------
@@ -391,25 +441,30 @@ cudaError_t dispatch_ldg(const OiScanParams &p, uint32_t grid, cudaStream_t st) 
   }
 }
 
+// tile = a multiple of 32 rows (2 rows x 16 consumer warps) of at most 48 KB (16 rows for very wide rows); ring of <= 8 stages in 200 KB
+static inline void bulk_tile_shape(uint32_t row_bytes, uint32_t *tile_rows, uint32_t *n_stages) {
+  uint32_t tr = (49152u / row_bytes) & ~31u;
+  if (tr < 16) tr = 16;
+  if (tr > 256) tr = 256;
+  uint32_t ns = (uint32_t)((200u * 1024u) / (tr * row_bytes));
+  if (ns > 8) ns = 8;
+  *tile_rows = tr;
+  *n_stages = ns;
+}
+
 template <typename T, int NVL>
 cudaError_t launch_bulk(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
   const uint32_t row_bytes = p.nv * 16u;
-  uint32_t tile_rows = (32768u / row_bytes) & ~7u;
-  if (tile_rows < 8) tile_rows = 8;
-  if (tile_rows > 256) tile_rows = 256;
-  const uint32_t tile_bytes = tile_rows * row_bytes;
-  const size_t budget = 200 * 1024;
-  uint32_t n_stages = (uint32_t)(budget / tile_bytes);
-  if (n_stages > 8) n_stages = 8;
+  uint32_t tile_rows, n_stages;
+  bulk_tile_shape(row_bytes, &tile_rows, &n_stages);
   if (n_stages < 2) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)n_stages * tile_bytes + 2 * n_stages * sizeof(u64);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cosine_scan_bulk_kernel<T, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  cosine_scan_bulk_kernel<T, NVL><<<grid, kConsumerThreads + 32, smem, st>>>(p, tile_rows, n_stages);
+  const size_t smem = (size_t)n_stages * tile_rows * row_bytes + 2 * n_stages * sizeof(u64) + n_stages * sizeof(uint32_t);
+  const bool exact = p.nv == 32u * NVL;
+  cudaError_t e = exact ? cudaFuncSetAttribute(cosine_scan_bulk_kernel<T, NVL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(cosine_scan_bulk_kernel<T, NVL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (exact) cosine_scan_bulk_kernel<T, NVL, true><<<grid, kBulkThreads + 32, smem, st>>>(p, tile_rows, n_stages);
+  else cosine_scan_bulk_kernel<T, NVL, false><<<grid, kBulkThreads + 32, smem, st>>>(p, tile_rows, n_stages);
   return cudaGetLastError();
 }
 
@@ -478,27 +533,54 @@ cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_
   p.nv = dim * esize / 16u;
   p.doc_base = doc_base;
   p.k = k;
-  // grid: one (bulk) or two (ldg) CTAs per SM, but never fewer than 64 rows per CTA
-  uint32_t grid = variant == 1 ? (uint32_t)num_sms : (uint32_t)num_sms * 2u;
-  const uint32_t max_useful = (uint32_t)((n_rows + 63) / 64);
-  if (grid > max_useful) grid = max_useful ? max_useful : 1;
-  if (grid > ws.max_grid) grid = ws.max_grid;
-  uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
-  rpc = (rpc + 31u) & ~31u;
-  p.rows_per_cta = rpc;
-  grid = (uint32_t)((n_rows + rpc - 1) / rpc);
-  if (grid == 0) grid = 1;
+  const bool bulk = variant == 1 && p.nv <= 256;
+  uint32_t grid;
+  if (bulk) {
+    // one CTA per SM pulling tiles from a counter; never more CTAs than tiles
+    uint32_t tile_rows, n_stages;
+    bulk_tile_shape(p.nv * 16u, &tile_rows, &n_stages);
+    const uint32_t n_tiles = (uint32_t)((n_rows + tile_rows - 1) / tile_rows);
+    grid = (uint32_t)num_sms;
+    if (grid > n_tiles) grid = n_tiles ? n_tiles : 1;
+    if (grid > ws.max_grid) grid = ws.max_grid;
+    p.rows_per_cta = 0;
+  } else {
+    // two CTAs per SM, each a contiguous row range, but never fewer than 64 rows per CTA
+    grid = (uint32_t)num_sms * 2u;
+    const uint32_t max_useful = (uint32_t)((n_rows + 63) / 64);
+    if (grid > max_useful) grid = max_useful ? max_useful : 1;
+    if (grid > ws.max_grid) grid = ws.max_grid;
+    uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
+    rpc = (rpc + 31u) & ~31u;
+    p.rows_per_cta = rpc;
+    grid = (uint32_t)((n_rows + rpc - 1) / rpc);
+    if (grid == 0) grid = 1;
+  }
+  p.cand_stride = ws.max_grid * ws.k_stride;
+  if (bulk) {
+    // one persistent launch walks the whole batch: the epilogue (list merge) of query i overlaps
+    // the streaming of query i+1
+    p.nq = nq;
+    p.q = d_queries;
+    p.cand = ws.cand;
+    p.gthr = ws.gthr;
+    p.ticket = ws.ticket;
+    p.tile_ctr = ws.tile_ctr;
+    p.out_keys = d_out_keys;
+    cudaError_t e = dtype == OI_DTYPE_F32 ? dispatch_bulk<float>(p, grid, stream) : dispatch_bulk<__nv_bfloat16>(p, grid, stream);
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    return cudaSuccess;
+  }
+  p.nq = 1;
   for (uint32_t qi = 0; qi < nq; ++qi) {
     p.q = d_queries + (size_t)qi * dim;
-    p.cand = ws.cand + (size_t)qi * ws.max_grid * ws.k_stride;
+    p.cand = ws.cand + (size_t)qi * p.cand_stride;
     p.gthr = ws.gthr + qi;
     p.ticket = ws.ticket + qi;
+    p.tile_ctr = ws.tile_ctr + qi;
     p.out_keys = d_out_keys + (size_t)qi * k;
-    cudaError_t e;
-    if (variant == 1 && p.nv <= 256)
-      e = dtype == OI_DTYPE_F32 ? dispatch_bulk<float>(p, grid, stream) : dispatch_bulk<__nv_bfloat16>(p, grid, stream);
-    else
-      e = dtype == OI_DTYPE_F32 ? dispatch_ldg<float>(p, grid, stream) : dispatch_ldg<__nv_bfloat16>(p, grid, stream);
+    cudaError_t e = dtype == OI_DTYPE_F32 ? dispatch_ldg<float>(p, grid, stream) : dispatch_ldg<__nv_bfloat16>(p, grid, stream);
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
   }

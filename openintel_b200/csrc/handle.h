@@ -16,7 +16,7 @@ struct oi_index {
   // embeddings
   void *d_emb = nullptr;
   uint64_t emb_rows_loaded = 0;
-  int cosine_variant = 0;
+  int cosine_variant = 1;  // 0 = direct loads, 1 = bulk-copy pipeline with dynamic tiles
 
   // per-call workspaces (device)
   OiCosineWorkspace cws;

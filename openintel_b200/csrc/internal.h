@@ -25,13 +25,18 @@ struct OiScanParams {
   u64 *cand;           // [grid][k] per-CTA sorted candidates
   u64 *gthr;           // grid-wide lower bound of the k-th best key (reset to 0 by the last CTA)
   uint32_t *ticket;    // last-CTA election counter (reset to 0 by the last CTA)
+  uint32_t *tile_ctr;  // dynamic tile counter of the bulk variant (reset to 0 by the last CTA)
   u64 *out_keys;       // [k] final sorted keys (0 = empty)
+  // batch form (bulk variant: one persistent launch walks nq queries; pointers above = query 0)
+  uint32_t nq;
+  uint32_t cand_stride;  // keys between two queries' candidate areas
 };
 
 struct OiCosineWorkspace {
   u64 *cand = nullptr;       // [max_batch][max_grid][k_stride]
   u64 *gthr = nullptr;       // [max_batch]
   uint32_t *ticket = nullptr;  // [max_batch]
+  uint32_t *tile_ctr = nullptr;  // [max_batch]
   uint32_t max_grid = 0;
   uint32_t k_stride = 0;     // = max_k of the index
 };

@@ -1,0 +1,126 @@
+#!/usr/bin/env python3
+"""Secondary workloads of BASELINE.json (the headline bench is bench.py): device-timed throughput
+of the BM25 kernel at config 3 scale, the hybrid path and the batched cosine path, one JSON line
+per workload.  Single GPU.  Results are copied into profiles/ by hand.
+
+    python tools/bench_workloads.py bm25 [--docs 10000000 --vocab 1000000 --batch 1024]
+    python tools/bench_workloads.py hybrid [--docs 1000000 --dim 384 --batch 16]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SEED = 20261018
+
+
+def _time(fn, steps, warmup):
+    import torch
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_bm25(a):
+    import torch
+    import openintel_b200 as oi
+    import oracle as O
+    dev = torch.device("cuda", 0)
+    cdf = O.zipf_cdf(a.vocab)
+    t0 = time.perf_counter()
+    ix = oi.GpuIndex(n_docs=a.docs, dim=8, max_k=a.k, max_batch=a.batch)
+    ix.synth_bm25(SEED, a.vocab, cdf)
+    ix.bm25_finalize()
+    build_s = time.perf_counter() - t0
+    df, sdl, npost = ix.bm25_local_stats()
+    if a.groups:
+        ix.set_option("bm25_variant", a.groups)
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, uniform in (("zipf", False), ("uniform", True)):
+        n_pool = 4
+        pools = [O.synth_query_terms(a.batch, 8, cdf, uniform=uniform, first=p * a.batch) for p in range(n_pool)]
+        touched = float(np.mean([df[p].astype(np.int64).sum(axis=1).mean() for p in pools]))
+        d_terms = [torch.from_numpy(p.astype(np.int32).reshape(-1)).to(dev) for p in pools]
+        d_offs = torch.arange(0, a.batch * 8 + 1, 8, dtype=torch.int32, device=dev)
+        d_ids = torch.empty(a.batch, a.k, dtype=torch.int32, device=dev)
+        d_sc = torch.empty(a.batch, a.k, dtype=torch.float32, device=dev)
+        l0 = ix.launch_count()
+        ms = _time(lambda i: ix.search_bm25_dev(d_terms[i % n_pool], d_offs, a.batch, a.k, d_ids, d_sc, stream), a.steps, a.warmup)
+        launches = ix.launch_count() - l0
+        # e2e through the host-buffer call
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            ix.search_bm25(pools[i % n_pool], a.k)
+        e2e_ms = (time.perf_counter() - t0) / a.steps * 1e3
+        qps = a.batch / (ms * 1e-3)
+        print(json.dumps({
+            "workload": "configs[2]: BM25, %d docs, %d-term Zipf vocab, 8-term %s queries, batch %d, top-%d" % (a.docs, a.vocab, name, a.batch, a.k),
+            "value": qps, "unit": "queries/s", "ms_per_batch": ms, "e2e_queries_per_s": a.batch / (e2e_ms * 1e-3),
+            "postings": int(npost), "postings_touched_per_query": touched,
+            "algorithmic_GBps": touched * 8 * qps / 1e9, "index_build_s": build_s, "launches_per_batch": launches / (a.steps + a.warmup),
+            "groups_override": a.groups}), flush=True)
+    ix.close()
+
+
+def bench_hybrid(a):
+    import torch
+    import openintel_b200 as oi
+    import oracle as O
+    dev = torch.device("cuda", 0)
+    cdf = O.zipf_cdf(a.vocab)
+    ix = oi.GpuIndex(n_docs=a.docs, dim=a.dim, max_k=a.k, max_batch=a.batch)
+    ix.synth_embeddings(SEED)
+    ix.synth_bm25(SEED, a.vocab, cdf)
+    ix.bm25_finalize()
+    g = torch.Generator().manual_seed(7)
+    qv = torch.randn(4, a.batch, a.dim, generator=g)
+    qv = (qv / qv.norm(dim=2, keepdim=True)).to(dev)
+    qt = [torch.from_numpy(O.synth_query_terms(a.batch, 8, cdf, first=p * a.batch).astype(np.int32).reshape(-1)).to(dev) for p in range(4)]
+    d_offs = torch.arange(0, a.batch * 8 + 1, 8, dtype=torch.int32, device=dev)
+    outs = [torch.empty(a.batch, a.k, dtype=torch.int32, device=dev) for _ in range(3)]
+    d_rrf = torch.empty(a.batch, a.k, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = _time(lambda i: ix.search_hybrid_dev(qv[i % 4], qt[i % 4], d_offs, a.batch, a.k, 60, outs[0], d_rrf, outs[1], outs[2], stream), a.steps, a.warmup)
+    ms_cos = _time(lambda i: ix.search_cosine_dev(qv[i % 4], a.batch, a.k, outs[0], d_rrf, stream), a.steps, a.warmup)
+    ms_bm = _time(lambda i: ix.search_bm25_dev(qt[i % 4], d_offs, a.batch, a.k, outs[0], d_rrf, stream), a.steps, a.warmup)
+    print(json.dumps({"workload": "hybrid BM25+cosine+RRF top-%d, %d docs x %d f32, vocab %d, batch %d" % (a.k, a.docs, a.dim, a.vocab, a.batch),
+                      "value": a.batch / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "ms_cosine_only": ms_cos, "ms_bm25_only": ms_bm}), flush=True)
+    ix.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workload", choices=["bm25", "hybrid"])
+    ap.add_argument("--docs", type=int, default=None)
+    ap.add_argument("--vocab", type=int, default=1000000)
+    ap.add_argument("--dim", type=int, default=384)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--groups", type=int, default=0)
+    a = ap.parse_args()
+    if a.workload == "bm25":
+        a.docs = a.docs or 10_000_000
+        a.batch = a.batch or 1024
+        bench_bm25(a)
+    else:
+        a.docs = a.docs or 1_000_000
+        a.batch = a.batch or 16
+        bench_hybrid(a)
+
+
+if __name__ == "__main__":
+    main()
