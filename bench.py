@@ -119,6 +119,14 @@ def _synth_rows_parallel(O, n, dim, threads):
     return out
 
 
+def _traffic(key):
+    """dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def cpu_baseline_leg(rows, budget_s=12.0):
     """Times the oracle's multi-threaded f32 scan + top-k on this box's host cores, on a bounded
     sample: as many full single-query passes over the same 1M x 384 matrix as fit the budget."""
@@ -318,7 +326,9 @@ def main():
                     "d2h_bytes_per_step": QUERIES_PER_STEP * TOPK * 8, "timing": "wall clock around blocking C-ABI calls, max over ranks"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "traffic": _traffic("cosine_scan_bulk_f32_1Mx384_q16") if (world == 1 and not per_query_launch) else None,
+                         "traffic_source": "profiles/r01_ncu_cosine_scan_bulk.md (ncu --set full, same kernel and shape)",
+                         "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel": "cosine_scan_*_kernel", "bytes_per_launch": bytes_per_launch,
                          "avg_launch_us": avg_launch_s * 1e6,
                          "note": "avg launch = timed region / scan launches (includes unpack + launch gaps)"},

@@ -12,14 +12,14 @@ for v in 0 1; do
   cat gpurun_out/bench_v$v.json; tail -3 gpurun_out/bench_v$v.err
 done
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-  V=${NCU_VARIANT:-0}
+  V=${NCU_VARIANT:-1}; SKIP=${NCU_SKIP:-3}
   echo "== ncu (variant $V)"
   timeout 300 python bench.py --variant $V --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
       python bench.py --variant $V --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?"
   timeout 300 python bench.py --variant $V --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:cosine_scan -s 40 -c 2 -f -o gpurun_out/prof_scan_v$V \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:cosine_scan -s $SKIP -c 1 -f -o gpurun_out/prof_scan_v$V \
       python bench.py --variant $V --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"
 fi
