@@ -145,8 +145,12 @@ oi_status oi_lexicon_analyze(int32_t device, const uint8_t *texts, const uint64_
 /* ---- tuning / introspection (bench + tests) ------------------------------------------------ */
 /* number of kernels this handle has launched since creation (bench "gpu_launches") */
 uint64_t oi_index_launch_count(const oi_index *h);
-/* named integer knobs, e.g. "cosine_variant" (0 = ldg, 1 = bulk-copy pipeline) */
+/* named integer knobs: "cosine_variant" (0 = ldg, 1 = bulk-copy pipeline), "cosine_gemm_min_batch"
+ * (bf16 batches of at least this many queries take the tcgen05 tensor-core path; 0 = never),
+ * "cosine_gemm_cap" / "cosine_gemm_sample_tiles" (tests: force list compaction / the two-pass flow) */
 oi_status oi_index_set_option(oi_index *h, const char *name, int64_t value);
+/* tests: the raw nq x n_docs f32 score matrix of the tensor-core path (bf16 index, small shards) */
+oi_status oi_debug_cosine_gemm_scores(oi_index *h, const float *queries, uint32_t nq, float *out_scores);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,7 @@ def load_library():
         "oi_lexicon_analyze": (st, [C.c_int32, _vp, _u64p, C.c_uint64, _vp, _vp, _u32p, _u32p]),
         "oi_index_launch_count": (C.c_uint64, [H]),
         "oi_index_set_option": (st, [H, C.c_char_p, C.c_int64]),
+        "oi_debug_cosine_gemm_scores": (st, [H, _f32p, C.c_uint32, _f32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the .so does not export what the header declares
@@ -254,6 +255,13 @@ class GpuIndex:
     def search_hybrid_dev(self, d_queries, d_terms, d_offs, nq, k, rrf_k, d_ids, d_rrf, d_rc, d_rb, stream=0):
         self._ck(self.L.oi_search_hybrid_dev(self.h, _addr(d_queries), _addr(d_terms), _addr(d_offs), nq, k, rrf_k,
                                              _addr(d_ids), _addr(d_rrf), _addr(d_rc), _addr(d_rb), stream))
+
+    def debug_cosine_gemm_scores(self, queries):
+        """tests: raw nq x n_docs score matrix of the tensor-core path"""
+        queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        out = np.empty((queries.shape[0], self.n_docs), dtype=np.float32)
+        self._ck(self.L.oi_debug_cosine_gemm_scores(self.h, _addr(queries), queries.shape[0], _addr(out)))
+        return out
 
     def launch_count(self):
         return int(self.L.oi_index_launch_count(self.h))

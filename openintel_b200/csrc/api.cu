@@ -114,6 +114,7 @@ extern "C" void oi_index_destroy(oi_index *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   oi_comm_destroy(h);
   oi_bm25_free(h);
+  oi_gemm_free(h);
   cudaFree(h->d_emb);
   cudaFree(h->cws.cand);
   cudaFree(h->cws.gthr);
@@ -138,6 +139,21 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
   if (!strcmp(name, "cosine_variant")) {
     OI_REQUIRE(value == 0 || value == 1, "cosine_variant must be 0 (ldg) or 1 (bulk pipeline)");
     h->cosine_variant = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "cosine_gemm_min_batch")) {
+    OI_REQUIRE(value >= 0 && value <= 65536, "cosine_gemm_min_batch must be in 0..65536 (0 = tensor-core path off)");
+    h->gemm_min_batch = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "cosine_gemm_cap")) {
+    OI_REQUIRE(value == 0 || value == 128 || value == 256 || value == 512, "cosine_gemm_cap must be 0, 128, 256 or 512");
+    h->gemm_cap = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "cosine_gemm_sample_tiles")) {
+    OI_REQUIRE(value >= 0 && value <= 7, "cosine_gemm_sample_tiles must be in 0..7");
+    h->gemm_sample_tiles = (int)value;
     return OI_OK;
   }
   if (!strcmp(name, "bm25_variant")) {
@@ -196,8 +212,14 @@ static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, u
   if (h->emb_rows_loaded < h->desc.n_docs) return h->fail(OI_ERR_STATE, "embeddings not loaded (%llu of %llu rows)", (unsigned long long)h->emb_rows_loaded, (unsigned long long)h->desc.n_docs);
   if (nq == 0) return OI_OK;
   u64 *local = h->world > 1 ? h->d_keys_local : h->d_keys_cos;
-  OI_CK(oi_launch_cosine_scan(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, (uint32_t)h->desc.doc_base, d_queries, nq, k,
-                              h->cws, local, h->cosine_variant, h->num_sms, st, &h->launches));
+  if (h->gemm_min_batch > 0 && nq >= (uint32_t)h->gemm_min_batch && oi_gemm_eligible(h, nq, k)) {
+    // batched bf16 queries: one pass of the matrix through the tensor cores serves the whole batch
+    oi_status s = oi_gemm_local_keys(h, d_queries, nq, k, local, nullptr, st);
+    if (s) return s;
+  } else {
+    OI_CK(oi_launch_cosine_scan(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, (uint32_t)h->desc.doc_base, d_queries, nq, k,
+                                h->cws, local, h->cosine_variant, h->num_sms, st, &h->launches));
+  }
   if (h->world > 1) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_cos, st);
   return OI_OK;
 }
@@ -232,6 +254,28 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
   OI_CK(cudaMemcpyAsync(out_ids, h->d_out_u32, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaMemcpyAsync(out_scores, h->d_out_f32, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaStreamSynchronize(st));
+  return OI_OK;
+}
+
+extern "C" oi_status oi_debug_cosine_gemm_scores(oi_index *h, const float *queries, uint32_t nq, float *out_scores) {
+  if (!h) return OI_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  OI_REQUIRE(queries && out_scores && nq >= 1 && nq <= h->desc.max_batch, "bad arguments");
+  if (!oi_gemm_eligible(h, nq, 1)) return h->fail(OI_ERR_UNSUPPORTED, "tensor-core path needs a bf16 index with dim %% 64 == 0 and dim <= 768");
+  if (h->emb_rows_loaded < h->desc.n_docs) return h->fail(OI_ERR_STATE, "embeddings not loaded");
+  OI_CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = h->stream;
+  float *d_dump = nullptr;
+  const size_t n = (size_t)nq * h->desc.n_docs;
+  OI_CK(cudaMalloc(&d_dump, n * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(h->d_queries, queries, (size_t)nq * h->desc.dim * sizeof(float), cudaMemcpyHostToDevice, st);
+  oi_status s = OI_OK;
+  if (e == cudaSuccess) s = oi_gemm_local_keys(h, h->d_queries, nq, 1, h->d_keys_cos, d_dump, st);
+  if (e == cudaSuccess && s == OI_OK) e = cudaMemcpyAsync(out_scores, d_dump, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && s == OI_OK) e = cudaStreamSynchronize(st);
+  cudaFree(d_dump);
+  if (s) return s;
+  OI_CK(e);
   return OI_OK;
 }
 

@@ -4,6 +4,7 @@
 
 struct OiBm25;  // bm25.cu
 struct OiComm;  // comm.cu
+struct OiGemm;  // cosine_gemm.cu
 
 struct oi_index {
   oi_index_desc desc{};
@@ -29,6 +30,12 @@ struct oi_index {
   uint32_t *d_out_u32 = nullptr;  // 3 x [max_batch][max_k]
   float *d_out_f32 = nullptr;     // [max_batch][max_k]
 
+  // batched cosine on the tensor cores (cosine_gemm.cu); workspace is created on first use
+  OiGemm *gemm = nullptr;
+  int gemm_min_batch = 4;      // batches of at least this many queries take the tcgen05 path (0 = never)
+  int gemm_cap = 0;            // tests: candidate-list capacity override (0 = default)
+  int gemm_sample_tiles = 0;   // tests: sample-pass tiles per CTA override (0 = default)
+
   // BM25
   OiBm25 *bm25 = nullptr;
   int bm25_variant = 0;
@@ -48,6 +55,13 @@ uint32_t *oi_bm25_stage_offs(oi_index *h);
 // prep -> blocked scoring -> merge: shard-local sorted key lists d_out_keys[nq][k] (global doc ids)
 oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint32_t *d_q_offs, uint32_t nq,
                              uint32_t k, u64 *d_out_keys, cudaStream_t st);
+// cosine_gemm.cu
+void oi_gemm_free(oi_index *h);
+bool oi_gemm_eligible(const oi_index *h, uint32_t nq, uint32_t k);
+// shard-local sorted key lists d_out_keys[nq][k] of nq f32 device queries; d_dump (tests) receives the
+// raw nq x n_docs score matrix when not NULL
+oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, u64 *d_out_keys, float *d_dump,
+                             cudaStream_t st);
 // comm.cu
 void oi_comm_destroy(oi_index *h);
 // all-gathers each rank's [nq][k] local lists and merges them into d_out [nq][k] on every rank
