@@ -146,6 +146,14 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->gemm_min_batch = (int)value;
     return OI_OK;
   }
+  if (!strcmp(name, "cosine_gemm_force_2d")) {
+    h->gemm_force_2d = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "cosine_gemm_debug")) {
+    h->gemm_debug = (int)value;
+    return OI_OK;
+  }
   if (!strcmp(name, "cosine_gemm_cap")) {
     OI_REQUIRE(value == 0 || value == 128 || value == 256 || value == 512, "cosine_gemm_cap must be 0, 128, 256 or 512");
     h->gemm_cap = (int)value;

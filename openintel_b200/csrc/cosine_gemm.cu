@@ -39,11 +39,13 @@ struct OiGemm {
   __nv_bfloat16 *d_qb = nullptr;  // [n_qt_max * 128][dim] bf16 query tiles (zero padded)
   u64 *d_cand = nullptr;          // [max_lists][cap]
   uint32_t *d_cnt = nullptr;      // [max_lists]
-  u64 *d_keys_a = nullptr;        // [max_batch][max_k] sample-pass result
+  u64 *d_keys_a = nullptr;        // [max_batch][max_k] running result after a pass (ping)
+  u64 *d_keys_b = nullptr;        // (pong)
   u64 *d_thr_a = nullptr;         // [max_batch]
   uint32_t cap = 0;
   size_t max_lists = 0;
   CUtensorMap tmap;
+  bool tma3d = false;
   bool ready = false;
 };
 
@@ -52,8 +54,6 @@ namespace {
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kTileDocs = 64;    // MMA N: documents per tile
 constexpr uint32_t kKBlock = 64;      // bf16 elements per box row (128 B)
-constexpr uint32_t kStageBytes = kTileDocs * 128;
-constexpr uint32_t kStages = 20;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kDCol0 = 384;      // two 64-column accumulators at 384 and 448
 constexpr uint32_t kCapMax = 512;     // keys per (CTA, query) candidate list
@@ -68,6 +68,8 @@ struct GemmParams {
   uint32_t *cand_cnt;             // [grid * 128]
   uint32_t cap;
   float *dump;                    // tests: [nq][n_rows] raw scores, or nullptr
+  uint32_t tma3d;                 // the tensor map is the 3-D (k-block-major) view: one TMA op per stage
+  uint32_t debug;                 // timing experiments: bit 0 = no MMA issue, bit 1 = no TMA loads, bit 2 = no score filter (results are garbage)
 };
 
 __device__ __forceinline__ void warp_bitonic_desc(u64 *buf, uint32_t n, int lane) {
@@ -99,26 +101,55 @@ __device__ __forceinline__ u64 warp_compact_list(u64 *list, uint32_t n, uint32_t
   return thr;
 }
 
+// Ring geometry for a row of NKB k-blocks (dim = 64 * NKB): the 192 KB ring holds 24 slabs of
+// 64 rows x 128 B.  A stage = KBS slabs (one TMA op, one mbarrier); a tile = SPT stages; the ring
+// holds TIF whole tiles, so inside a group of TIF tiles every stage index is a compile-time constant.
+template <int NKB>
+struct GemmShape {
+  static_assert(24 % NKB == 0, "dim / 64 must divide 24");
+  static constexpr int KBS = (NKB % 4 == 0) ? 4 : (NKB % 2 == 0) ? 2 : 1;
+  static constexpr int SPT = NKB / KBS;
+  static constexpr int TIF = 24 / NKB;
+  static constexpr int STAGES = SPT * TIF;
+  static constexpr uint32_t STAGE_BYTES = KBS * 8192u;
+};
+constexpr uint32_t kRingBytes = 24 * 8192;
+constexpr uint32_t kMaxStages = 24;
+
+__device__ __forceinline__ uint32_t oi_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+
+template <int NKB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     cosine_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+  using Sh = GemmShape<NKB>;
+  constexpr int KBS = Sh::KBS, SPT = Sh::SPT, TIF = Sh::TIF, STAGES = Sh::STAGES;
   extern __shared__ unsigned char s_raw[];
   unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char *s_stage = sm;                                                   // kStages x 8 KB, 1024 B aligned
-  u64 *s_scratch = reinterpret_cast<u64 *>(sm + kStages * kStageBytes);          // 4 warps x cap keys
+  unsigned char *s_stage = sm;                                                   // 24 slabs x 8 KB, 1024 B aligned
+  u64 *s_scratch = reinterpret_cast<u64 *>(sm + kRingBytes);                     // 4 warps x cap keys
   u64 *s_full = s_scratch + 4 * kCapMax;
-  u64 *s_empty = s_full + kStages;
-  u64 *s_tfull = s_empty + kStages;   // [2] accumulator ready
-  u64 *s_tempty = s_tfull + 2;        // [2] accumulator drained
+  u64 *s_empty = s_full + kMaxStages;
+  u64 *s_tfull = s_empty + kMaxStages;  // [2] accumulator ready
+  u64 *s_tempty = s_tfull + 2;          // [2] accumulator drained
   u64 *s_qready = s_tempty + 2;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_qready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t qt = blockIdx.x % p.n_qt, range = blockIdx.x / p.n_qt;
-  const uint32_t nkb = p.dim / kKBlock;
   const uint32_t t0 = p.tile_begin + range;
 
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < kStages; ++s) { oi_mbar_init(&s_full[s], 1); oi_mbar_init(&s_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { oi_mbar_init(&s_full[s], 1); oi_mbar_init(&s_empty[s], 1); }
     for (uint32_t b = 0; b < 2; ++b) { oi_mbar_init(&s_tfull[b], 1); oi_mbar_init(&s_tempty[b], 4); }
     oi_mbar_init(s_qready, 128);
     oi_mbar_fence_init();
@@ -129,46 +160,87 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   oi_tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
+  // Warps 0 and 1 run their loops warp-uniformly and only the elected lane issues the TMA / MMA /
+  // commit instructions: operands then live in uniform registers and one k-block costs a handful of
+  // instructions (a single issuing thread must spend < 32 cycles per N = 64 MMA).
   if (warp == 0) {
     // ------------------------------- TMA producer ------------------------------------------------
-    if (lane == 0) {
-      oi_tma_prefetch_desc(&tmap);
-      uint32_t it = 0;
-      for (uint32_t t = t0; t < p.tile_end; t += p.n_ranges) {
-        for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+    const bool leader = oi_elect_one();
+    if (leader) oi_tma_prefetch_desc(&tmap);
+    uint32_t grp = 0;
+    for (uint32_t tb = t0; tb < p.tile_end; tb += TIF * p.n_ranges, ++grp) {
+      const uint32_t ph = grp & 1u;
+#pragma unroll
+      for (int u = 0; u < TIF; ++u) {
+        const uint32_t t = tb + u * p.n_ranges;
+        if (t >= p.tile_end) break;
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+          const int s = u * SPT + j;
           oi_mbar_wait(&s_empty[s], ph ^ 1u);
-          oi_mbar_expect_tx(&s_full[s], kStageBytes);
-          // rows past the end of the shard are zero-filled by the TMA unit
-          oi_tma_load_2d(s_stage + (size_t)s * kStageBytes, &tmap, (int32_t)(kb * kKBlock), (int32_t)(t * kTileDocs), &s_full[s]);
+          if (leader) {
+            if (p.debug & 2u) {
+              oi_mbar_arrive(&s_full[s]);
+            } else {
+              oi_mbar_expect_tx(&s_full[s], Sh::STAGE_BYTES);
+              // rows past the end of the shard are zero-filled by the TMA unit
+              if (p.tma3d) {
+                oi_tma_load_3d(s_stage + (size_t)s * Sh::STAGE_BYTES, &tmap, 0, (int32_t)(t * kTileDocs), j * KBS, &s_full[s]);
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < KBS; ++kk)
+                  oi_tma_load_2d(s_stage + (size_t)s * Sh::STAGE_BYTES + kk * 8192, &tmap, (j * KBS + kk) * (int)kKBlock,
+                                 (int32_t)(t * kTileDocs), &s_full[s]);
+              }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = oi_umma_idesc_bf16(128, kTileDocs);
-      oi_mbar_wait(s_qready, 0);
-      oi_tc_fence_after();
-      uint32_t it = 0, tl = 0;
-      for (uint32_t t = t0; t < p.tile_end; t += p.n_ranges, ++tl) {
+    const bool leader = oi_elect_one();
+    constexpr uint32_t idesc = oi_umma_idesc_bf16(128, kTileDocs);
+    const uint64_t desc0 = oi_umma_smem_desc_sw128(oi_smem_u32(s_stage));
+    oi_mbar_wait(s_qready, 0);
+    oi_tc_fence_after();
+    uint32_t grp = 0, tl = 0;
+    for (uint32_t tb = t0; tb < p.tile_end; tb += TIF * p.n_ranges, ++grp) {
+      const uint32_t ph = grp & 1u;
+#pragma unroll
+      for (int u = 0; u < TIF; ++u) {
+        const uint32_t t = tb + u * p.n_ranges;
+        if (t >= p.tile_end) break;
         const uint32_t b = tl & 1u, bph = (tl >> 1) & 1u;
+        ++tl;
         oi_mbar_wait(&s_tempty[b], bph ^ 1u);
         oi_tc_fence_after();
         const uint32_t d_addr = tmem + kDCol0 + b * kTileDocs;
-        for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+          const int s = u * SPT + j;
           oi_mbar_wait(&s_full[s], ph);
           oi_tc_fence_after();
-          const uint64_t bdesc = oi_umma_smem_desc_sw128(oi_smem_u32(s_stage + (size_t)s * kStageBytes));
+          if (leader) {
+            if (p.debug & 1u) {
+              oi_mbar_arrive(&s_empty[s]);
+              if (j == SPT - 1) oi_mbar_arrive(&s_tfull[b]);
+            } else {
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) {
-            // A: 16 bf16 of K = 8 TMEM columns; B: 16 bf16 of K = 32 B inside the swizzle atom
-            oi_umma_ts_bf16(d_addr, tmem + (kb * 4 + ks) * 8, bdesc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < KBS; ++kk) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  // A: 16 bf16 of K = 8 TMEM columns; B: slab (s * KBS + kk), 32 B per k-step inside the swizzle atom
+                  const int kbi = j * KBS + kk;
+                  oi_umma_ts_bf16(d_addr, tmem + (uint32_t)((kbi * 4 + ks) * 8), desc0 + (uint64_t)((s * KBS + kk) * 512 + ks * 2), idesc,
+                                  (kbi | ks) != 0 ? 1u : 0u);
+                }
+              }
+              oi_umma_commit(&s_empty[s]);  // the stage is free once these MMAs have read it
+              if (j == SPT - 1) oi_umma_commit(&s_tfull[b]);
+            }
           }
-          oi_umma_commit(&s_empty[s]);  // the stage is free once these MMAs have read it
         }
-        oi_umma_commit(&s_tfull[b]);
       }
     }
   } else {
@@ -216,27 +288,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
       const uint32_t doc0 = t * kTileDocs;
       const uint32_t n_valid = min(kTileDocs, p.n_rows - doc0);
-      if (qv) {
+      if (n_valid < kTileDocs) {  // last tile of the shard: columns past the end never qualify
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if ((uint32_t)i >= n_valid) v[i] = 0x7FC00000u;  // NaN: loses every fmaxf and every >= compare
+      }
+      if (qv && !(p.debug & 4u)) {
         if (p.dump) {
 #pragma unroll
           for (int i = 0; i < 64; ++i)
             if ((uint32_t)i < n_valid) p.dump[(size_t)q * p.n_rows + doc0 + i] = __uint_as_float(v[i]);
         }
-        float m = -INFINITY;
-        if (n_valid == kTileDocs) {
+        // two-level filter: maxima of 8 groups of 8 scores, then their maximum.  Most tiles stop at
+        // the single compare; a tile with a survivor only opens the groups that hold one.
+        float gm[8];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) m = fmaxf(m, (uint32_t)i < n_valid ? __uint_as_float(v[i]) : -INFINITY);
+        for (int g = 0; g < 8; ++g) {
+          const float a = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+          const float b = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
+          gm[g] = fmaxf(fmaxf(a, b), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
         }
+        const float m = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])), fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
         if (m >= thr_s) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float s = __uint_as_float(v[i]);
-            if (s >= thr_s && (uint32_t)i < n_valid) {
-              const u64 key = oi_make_key(s, p.doc_base + doc0 + i);
-              if (key > thr_key) { buf[cnt] = key; ++cnt; }
+          for (int g = 0; g < 8; ++g) {
+            if (gm[g] >= thr_s) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float s = __uint_as_float(v[8 * g + e]);
+                if (s >= thr_s) {
+                  const u64 key = oi_make_key(s, p.doc_base + doc0 + 8 * g + e);
+                  if (key > thr_key) { buf[cnt] = key; ++cnt; }
+                }
+              }
             }
           }
         }
@@ -284,41 +368,55 @@ struct MergeState {
 
 // One CTA per query: exact top-k over the query's n_ranges candidate lists (+ an optional sorted
 // list from an earlier pass).  out[q][k] sorted descending; thr_out[q] = k-th key or 0.
+constexpr uint32_t kMergeMaxLists = 1024;
 __global__ void __launch_bounds__(256) gemm_merge_kernel(const u64 *cand, const uint32_t *cnts, uint32_t cap, uint32_t n_ranges,
                                                          uint32_t n_qt, uint32_t k, const u64 *prev, u64 *out, u64 *thr_out) {
   __shared__ MergeState S;
-  const int tid = threadIdx.x;
+  __shared__ uint32_t s_cnt[kMergeMaxLists];
+  __shared__ uint32_t s_hi;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t q = blockIdx.x, qt = q / 128, rl = q % 128;
-  if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
+  for (uint32_t r = tid; r < n_ranges; r += 256) s_cnt[r] = min(cnts[((size_t)r * n_qt + qt) * 128 + rl], cap);
+  // the earlier pass's list is already the best k of its documents: it seeds the buffer
+  uint32_t seed = 0;
+  if (prev) {
+    for (uint32_t i = tid; i < k; i += 256) S.buf[i] = prev[(size_t)q * k + i];
+    seed = k;
+  }
+  if (tid == 0) { S.cnt = seed; S.thr = 0ull; }
   __syncthreads();
-  const uint32_t n_list = n_ranges * cap;
-  const uint32_t total = n_list + (prev ? k : 0u);
-  uint32_t base = 0;
-  while (base < total) {
-    const uint32_t span = min(total - base, (uint32_t)OI_SEL_CAP - S.cnt);
+  if (prev) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);  // drops empty (0) keys, sets thr when k are held
+  uint32_t r0 = 0;
+  while (r0 < n_ranges) {
+    if (tid == 0) {  // as many whole lists as the buffer can absorb in the worst case
+      const uint32_t budget = (uint32_t)OI_SEL_CAP - S.cnt;
+      uint32_t r1 = r0, sum = 0;
+      while (r1 < n_ranges && sum + s_cnt[r1] <= budget) sum += s_cnt[r1++];
+      s_hi = r1;
+    }
+    __syncthreads();
+    const uint32_t r1 = s_hi;
     const u64 thr = S.thr;
     __syncthreads();
-    for (uint32_t i = base + tid; i < base + span; i += 256) {
-      u64 key;
-      if (i < n_list) {
-        const uint32_t r = i / cap, j = i % cap;
-        const size_t L = ((size_t)r * n_qt + qt) * 128 + rl;
-        key = j < cnts[L] ? __ldcg(cand + L * cap + j) : 0ull;
-      } else {
-        key = prev[(size_t)q * k + (i - n_list)];
+    for (uint32_t r = r0 + warp; r < r1; r += 8) {
+      const u64 *list = cand + (((size_t)r * n_qt + qt) * 128 + rl) * cap;
+      const uint32_t n = s_cnt[r];
+      for (uint32_t j = lane; j < n; j += 32) {
+        const u64 key = __ldcg(list + j);
+        if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
       }
-      if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
     }
-    base += span;
+    r0 = r1;
     __syncthreads();
-    if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
+    if (S.cnt > OI_SEL_CAP / 2 || r0 >= n_ranges) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
   }
+  if (n_ranges == 0) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
   for (uint32_t i = tid; i < k; i += 256) out[(size_t)q * k + i] = i < S.cnt ? S.buf[i] : 0ull;
   if (thr_out && tid == 0) thr_out[q] = S.cnt == k ? S.buf[k - 1] : 0ull;
 }
 
 size_t gemm_smem_bytes() {
-  return 1024 + (size_t)kStages * kStageBytes + 4 * kCapMax * sizeof(u64) + (2 * kStages + 5) * sizeof(u64) + 16;
+  return 1024 + (size_t)kRingBytes + 4 * kCapMax * sizeof(u64) + (2 * kMaxStages + 5) * sizeof(u64) + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -338,14 +436,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 void oi_gemm_free(oi_index *h) {
   OiGemm *g = h->gemm;
   if (!g) return;
-  cudaFree(g->d_qb); cudaFree(g->d_cand); cudaFree(g->d_cnt); cudaFree(g->d_keys_a); cudaFree(g->d_thr_a);
+  cudaFree(g->d_qb); cudaFree(g->d_cand); cudaFree(g->d_cnt); cudaFree(g->d_keys_a); cudaFree(g->d_keys_b); cudaFree(g->d_thr_a);
   delete g;
   h->gemm = nullptr;
 }
 
 bool oi_gemm_eligible(const oi_index *h, uint32_t nq, uint32_t k) {
   const uint32_t cap = h->gemm_cap ? (uint32_t)h->gemm_cap : kCapMax;
-  return h->desc.dtype == OI_DTYPE_BF16 && h->desc.dim % kKBlock == 0 && h->desc.dim <= kMaxDim && h->desc.n_docs > 0 &&
+  return h->desc.dtype == OI_DTYPE_BF16 && h->desc.dim % kKBlock == 0 && h->desc.dim <= kMaxDim &&
+         24 % (h->desc.dim / kKBlock) == 0 && h->desc.n_docs > 0 &&
          h->desc.n_docs < 0x7FFFFFC0ull && k + kTileDocs <= cap && nq >= 1;
 }
 
@@ -362,21 +461,45 @@ static oi_status gemm_prepare(oi_index *h) {
   GM_CK(cudaMalloc(&g->d_cand, g->max_lists * g->cap * sizeof(u64)));
   GM_CK(cudaMalloc(&g->d_cnt, g->max_lists * sizeof(uint32_t)));
   GM_CK(cudaMalloc(&g->d_keys_a, B * K * sizeof(u64)));
+  GM_CK(cudaMalloc(&g->d_keys_b, B * K * sizeof(u64)));
   GM_CK(cudaMalloc(&g->d_thr_a, B * sizeof(u64)));
 
   void *fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   GM_CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return h->fail(OI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-  const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)h->desc.n_docs};
-  const cuuint64_t gstride[1] = {(cuuint64_t)dim * sizeof(__nv_bfloat16)};
-  const cuuint32_t box[2] = {kKBlock, kTileDocs};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult cr = ((EncodeTiledFn)fn)(&g->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_emb, gdim, gstride, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return h->fail(OI_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
+  // 3-D view (64 elements, rows, k-blocks): one TMA op brings KBS consecutive 128 B column slabs of 64 rows,
+  // each landing as its own swizzled 8 KB slab.  If the driver rejects the view, fall back to one 2-D box per slab.
+  const uint32_t nkb = (uint32_t)(dim / kKBlock);
+  const uint32_t kbs = nkb % 4 == 0 ? 4 : nkb % 2 == 0 ? 2 : 1;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  {
+    const cuuint64_t gdim[3] = {kKBlock, (cuuint64_t)h->desc.n_docs, nkb};
+    const cuuint64_t gstride[2] = {(cuuint64_t)dim * sizeof(__nv_bfloat16), kKBlock * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[3] = {kKBlock, kTileDocs, kbs};
+    CUresult cr = ((EncodeTiledFn)fn)(&g->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, h->d_emb, gdim, gstride, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    g->tma3d = cr == CUDA_SUCCESS;
+  }
+  if (!g->tma3d || h->gemm_force_2d) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)h->desc.n_docs};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {kKBlock, kTileDocs};
+    CUresult cr = ((EncodeTiledFn)fn)(&g->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->d_emb, gdim, gstride, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return h->fail(OI_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
+    g->tma3d = false;
+  }
+  const int smem = (int)gemm_smem_bytes();
+  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   g->ready = true;
   return OI_OK;
 }
@@ -390,7 +513,20 @@ static oi_status gemm_launch(oi_index *h, uint32_t nq, uint32_t n_qt, uint32_t n
   p.k = k; p.nq = nq; p.n_qt = n_qt; p.n_ranges = n_ranges;
   p.tile_begin = tile_begin; p.tile_end = tile_end;
   p.thr_in = thr_in; p.cand = g->d_cand; p.cand_cnt = g->d_cnt; p.cap = cap; p.dump = dump;
-  cosine_gemm_kernel<<<n_ranges * n_qt, kGemmThreads, gemm_smem_bytes(), st>>>(g->tmap, p);
+  p.debug = (uint32_t)h->gemm_debug;
+  p.tma3d = g->tma3d ? 1u : 0u;
+  const uint32_t grid = n_ranges * n_qt;
+  const size_t smem = gemm_smem_bytes();
+  switch (h->desc.dim / kKBlock) {
+    case 1: cosine_gemm_kernel<1><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+    case 2: cosine_gemm_kernel<2><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+    case 3: cosine_gemm_kernel<3><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+    case 4: cosine_gemm_kernel<4><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+    case 6: cosine_gemm_kernel<6><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+    case 8: cosine_gemm_kernel<8><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+    case 12: cosine_gemm_kernel<12><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+    default: return h->fail(OI_ERR_UNSUPPORTED, "internal: dim %u has no tensor-core kernel", h->desc.dim);
+  }
   ++h->launches;
   GM_CK(cudaGetLastError());
   return OI_OK;
@@ -417,22 +553,28 @@ oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, u
     ++h->launches;
     GM_CK(cudaGetLastError());
   }
-  // sample pass: as many tiles per CTA as fit a list without compaction
-  uint32_t spr = (cap - kTileDocs) / kTileDocs;
-  if (h->gemm_sample_tiles > 0) spr = std::min<uint32_t>(spr, (uint32_t)h->gemm_sample_tiles);
-  uint32_t n_sample = n_ranges * spr;
-  if (d_dump || n_sample >= n_tiles) n_sample = n_tiles;
-  if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_sample, nullptr, d_dump, st))) return s;
-  const bool two = n_sample < n_tiles;
-  gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, two ? g->d_keys_a : d_out_keys,
-                                        two ? g->d_thr_a : nullptr);
-  ++h->launches;
-  GM_CK(cudaGetLastError());
-  if (two) {
-    if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, n_sample, n_tiles, g->d_thr_a, nullptr, st))) return s;
-    gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, g->d_keys_a, d_out_keys, nullptr);
+  // Passes of geometrically growing size.  The first covers as many tiles per CTA as fit a candidate list
+  // without compaction and runs without thresholds; each later pass starts from the exact k-th best key of
+  // everything scored so far, so the share of tiles in which any score passes the filter keeps shrinking.
+  uint32_t per_range = (cap - kTileDocs) / kTileDocs;
+  if (h->gemm_sample_tiles > 0) per_range = std::min<uint32_t>(per_range, (uint32_t)h->gemm_sample_tiles);
+  uint32_t done = 0;
+  const u64 *prev = nullptr;
+  u64 *bufs[2] = {g->d_keys_a, g->d_keys_b};
+  int flip = 0;
+  while (done < n_tiles) {
+    uint64_t n_pass = (uint64_t)n_ranges * per_range;
+    if (d_dump || done + n_pass + n_pass / 4 >= n_tiles) n_pass = n_tiles - done;
+    const bool last = done + n_pass == n_tiles;
+    if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, done, done + (uint32_t)n_pass, prev ? g->d_thr_a : nullptr, d_dump, st))) return s;
+    u64 *out = last ? d_out_keys : bufs[flip];
+    gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, prev, out, last ? nullptr : g->d_thr_a);
     ++h->launches;
     GM_CK(cudaGetLastError());
+    prev = out;
+    flip ^= 1;
+    done += (uint32_t)n_pass;
+    per_range *= 8;
   }
   return OI_OK;
 }

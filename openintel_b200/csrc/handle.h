@@ -34,6 +34,8 @@ struct oi_index {
   OiGemm *gemm = nullptr;
   int gemm_min_batch = 4;      // batches of at least this many queries take the tcgen05 path (0 = never)
   int gemm_cap = 0;            // tests: candidate-list capacity override (0 = default)
+  int gemm_force_2d = 0;       // tests: one 2-D TMA box per slab instead of the 3-D view
+  int gemm_debug = 0;          // timing experiments only (see GemmParams::debug)
   int gemm_sample_tiles = 0;   // tests: sample-pass tiles per CTA override (0 = default)
 
   // BM25

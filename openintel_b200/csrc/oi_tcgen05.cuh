@@ -98,3 +98,11 @@ __device__ __forceinline__ void oi_tma_load_2d(void *smem_dst, const CUtensorMap
       "l"(m), "r"(oi_smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D box at (c0, c1, c2): used with the (64 elements, rows, k-blocks) view of a row-major matrix
+__device__ __forceinline__ void oi_tma_load_3d(void *smem_dst, const CUtensorMap *m, int32_t c0, int32_t c1, int32_t c2, void *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          oi_smem_u32(smem_dst)),
+      "l"(m), "r"(oi_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}

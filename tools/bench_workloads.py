@@ -100,9 +100,50 @@ def bench_hybrid(a):
     ix.close()
 
 
+def bench_gemm(a):
+    """configs[3]: 10M docs x 768 bf16, batch 256, cosine top-100 on the tcgen05 path"""
+    import torch
+    import openintel_b200 as oi
+    dev = torch.device("cuda", 0)
+    ix = oi.GpuIndex(n_docs=a.docs, dim=a.dim, dtype=oi.DTYPE_BF16, max_k=a.k, max_batch=a.batch)
+    ix.synth_embeddings(SEED)
+    if a.debug:
+        ix.set_option("cosine_gemm_debug", a.debug)
+    g = torch.Generator().manual_seed(7)
+    qv = torch.randn(4, a.batch, a.dim, generator=g)
+    qv = (qv / qv.norm(dim=2, keepdim=True))
+    d_qv = qv.to(dev)
+    h_qv = qv.pin_memory()
+    d_ids = torch.empty(a.batch, a.k, dtype=torch.int32, device=dev)
+    d_sc = torch.empty(a.batch, a.k, dtype=torch.float32, device=dev)
+    h_ids = torch.empty(a.batch, a.k, dtype=torch.int32).pin_memory()
+    h_sc = torch.empty(a.batch, a.k, dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
+    l0 = ix.launch_count()
+    from bench import ClockSampler
+    cs = ClockSampler(0)
+    cs.start()
+    ms = _time(lambda i: ix.search_cosine_dev(d_qv[i % 4], a.batch, a.k, d_ids, d_sc, stream), a.steps, a.warmup)
+    clocks = cs.stop()
+    launches = (ix.launch_count() - l0) / (a.steps + a.warmup)
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        ix.search_cosine(h_qv[i % 4], a.k, h_ids, h_sc)
+    e2e_ms = (time.perf_counter() - t0) / a.steps * 1e3
+    bytes_ = a.docs * a.dim * 2
+    flops = 2.0 * a.docs * a.dim * a.batch
+    sc = h_sc.numpy()
+    assert a.debug or np.all(np.diff(sc, axis=1) <= 0)
+    print(json.dumps({"debug": a.debug, "workload": "configs[3]: %d docs x %d bf16, batch %d, cosine top-%d (tcgen05 GEMM path)" % (a.docs, a.dim, a.batch, a.k),
+                      "value": a.batch / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "e2e_queries_per_s": a.batch / (e2e_ms * 1e-3),
+                      "hbm_GBps": bytes_ / (ms * 1e-3) / 1e9, "tensor_TFLOPs": flops / (ms * 1e-3) / 1e12,
+                      "launches_per_batch": launches, "clocks": clocks}), flush=True)
+    ix.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("workload", choices=["bm25", "hybrid"])
+    ap.add_argument("workload", choices=["bm25", "hybrid", "gemm"])
     ap.add_argument("--docs", type=int, default=None)
     ap.add_argument("--vocab", type=int, default=1000000)
     ap.add_argument("--dim", type=int, default=384)
@@ -111,8 +152,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--groups", type=int, default=0)
+    ap.add_argument("--debug", type=int, default=0)
     a = ap.parse_args()
-    if a.workload == "bm25":
+    if a.workload == "gemm":
+        a.docs = a.docs or 10_000_000
+        a.batch = a.batch or 256
+        if a.dim == 384:
+            a.dim = 768
+        bench_gemm(a)
+    elif a.workload == "bm25":
         a.docs = a.docs or 10_000_000
         a.batch = a.batch or 1024
         bench_bm25(a)
