@@ -249,15 +249,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const uint32_t row = quarter * 32 + lane;
     const uint32_t lane_taddr = tmem + ((quarter * 32u) << 16);
     {
-      const uint4 *qrow = reinterpret_cast<const uint4 *>(p.qb + ((size_t)qt * 128 + row) * p.dim);
-      for (uint32_t c = 0; c < p.dim / 2; c += 32) {
+      // the prep kernel stored the tile as [quarter][32-column chunk][lane][32 x u32]: one chunk of one
+      // warp is 4 KB contiguous, 128 B per lane
+      const uint32_t n_chunks = p.dim / 64;
+      const uint4 *qsrc = reinterpret_cast<const uint4 *>(p.qb) + ((size_t)(qt * 4 + quarter) * n_chunks * 32 + lane) * 8;
+      uint4 x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __ldg(qsrc + j);
+      for (uint32_t ch = 0; ch < n_chunks; ++ch) {
         uint32_t r[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint4 x = __ldg(qrow + c / 4 + j);
-          r[4 * j] = x.x; r[4 * j + 1] = x.y; r[4 * j + 2] = x.z; r[4 * j + 3] = x.w;
+        for (int j = 0; j < 8; ++j) { r[4 * j] = x[j].x; r[4 * j + 1] = x[j].y; r[4 * j + 2] = x[j].z; r[4 * j + 3] = x[j].w; }
+        if (ch + 1 < n_chunks) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __ldg(qsrc + (size_t)(ch + 1) * 256 + j);
         }
-        oi_tmem_st32(lane_taddr + c, r);
+        oi_tmem_st32(lane_taddr + ch * 32, r);
       }
       oi_tmem_wait_st();
       oi_tc_fence_before();
@@ -351,12 +358,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 }
 
-// f32 queries -> bf16 (RNE, SPEC §2), padded with zero rows to a multiple of 128
-__global__ void gemm_prep_queries_kernel(const float *q, uint32_t nq, uint32_t rows, uint32_t dim, __nv_bfloat16 *qb) {
-  const size_t n = (size_t)rows * dim;
+// f32 queries -> bf16 pairs (RNE, SPEC §2), zero rows up to a multiple of 128, stored in the order the
+// epilogue warps feed tcgen05.st: [query tile][lane quarter][32-column chunk][lane][32 x u32], where 32-bit
+// column c of a row holds elements (2c, 2c + 1) with 2c in the low half.
+__global__ void gemm_prep_queries_kernel(const float *q, uint32_t nq, uint32_t rows, uint32_t dim, uint32_t *qb) {
+  const uint32_t n_chunks = dim / 64;
+  const size_t n = (size_t)rows * dim / 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / dim;
-    qb[i] = r < nq ? __float2bfloat16_rn(q[i]) : __float2bfloat16_rn(0.0f);
+    const uint32_t w = (uint32_t)(i & 31), lane = (uint32_t)((i >> 5) & 31);
+    const size_t rest = i >> 10;
+    const uint32_t chunk = (uint32_t)(rest % n_chunks);
+    const size_t tq = rest / n_chunks;  // tile * 4 + quarter
+    const size_t row = tq * 32 + lane;
+    const uint32_t c = chunk * 32 + w;
+    uint32_t packed = 0;
+    if (row < nq) {
+      const float2 f = *reinterpret_cast<const float2 *>(q + row * dim + 2 * c);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(f.x), hi = __float2bfloat16_rn(f.y);
+      packed = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+    }
+    qb[i] = packed;
   }
 }
 
@@ -366,18 +387,34 @@ struct MergeState {
   uint32_t cnt;
 };
 
-// One CTA per query: exact top-k over the query's n_ranges candidate lists (+ an optional sorted
-// list from an earlier pass).  out[q][k] sorted descending; thr_out[q] = k-th key or 0.
-constexpr uint32_t kMergeMaxLists = 1024;
+// One CTA per query: exact top-k over the query's n_ranges candidate lists (+ the sorted list of the
+// earlier passes).  out[q][k] sorted descending; thr_out[q] = k-th key or 0.  The lists are walked as
+// one flat key sequence (prefix sums of the list lengths in shared memory), a buffer-load at a time,
+// every thread holding up to 8 independent loads in flight.
+constexpr uint32_t kMergeMaxLists = 1020;
 __global__ void __launch_bounds__(256) gemm_merge_kernel(const u64 *cand, const uint32_t *cnts, uint32_t cap, uint32_t n_ranges,
                                                          uint32_t n_qt, uint32_t k, const u64 *prev, u64 *out, u64 *thr_out) {
   __shared__ MergeState S;
-  __shared__ uint32_t s_cnt[kMergeMaxLists];
-  __shared__ uint32_t s_hi;
+  __shared__ uint32_t s_pre[kMergeMaxLists + 4];
+  __shared__ uint32_t s_wsum[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t q = blockIdx.x, qt = q / 128, rl = q % 128;
-  for (uint32_t r = tid; r < n_ranges; r += 256) s_cnt[r] = min(cnts[((size_t)r * n_qt + qt) * 128 + rl], cap);
-  // the earlier pass's list is already the best k of its documents: it seeds the buffer
+  // exclusive prefix sums of the list lengths: thread t owns lists 4t .. 4t+3
+  uint32_t c[4], tsum = 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint32_t r = tid * 4 + u;
+    c[u] = r < n_ranges ? min(cnts[((size_t)r * n_qt + qt) * 128 + rl], cap) : 0u;
+    tsum += c[u];
+  }
+  uint32_t x = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_wsum[warp] = x;
+  // the earlier passes' list is already the best k of its documents: it seeds the buffer
   uint32_t seed = 0;
   if (prev) {
     for (uint32_t i = tid; i < k; i += 256) S.buf[i] = prev[(size_t)q * k + i];
@@ -385,34 +422,53 @@ __global__ void __launch_bounds__(256) gemm_merge_kernel(const u64 *cand, const 
   }
   if (tid == 0) { S.cnt = seed; S.thr = 0ull; }
   __syncthreads();
-  if (prev) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);  // drops empty (0) keys, sets thr when k are held
-  uint32_t r0 = 0;
-  while (r0 < n_ranges) {
-    if (tid == 0) {  // as many whole lists as the buffer can absorb in the worst case
-      const uint32_t budget = (uint32_t)OI_SEL_CAP - S.cnt;
-      uint32_t r1 = r0, sum = 0;
-      while (r1 < n_ranges && sum + s_cnt[r1] <= budget) sum += s_cnt[r1++];
-      s_hi = r1;
-    }
-    __syncthreads();
-    const uint32_t r1 = s_hi;
+  uint32_t excl = x - tsum;
+  for (int w = 0; w < warp; ++w) excl += s_wsum[w];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint32_t r = tid * 4 + u;
+    if (r <= n_ranges) s_pre[r] = excl;
+    excl += c[u];
+  }
+  __syncthreads();
+  if (prev) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);  // sets thr when k real keys are held
+  const uint32_t total = s_pre[n_ranges];
+  uint32_t f0 = 0;
+  while (f0 < total) {
+    const uint32_t len = min(total - f0, (uint32_t)OI_SEL_CAP - S.cnt);
     const u64 thr = S.thr;
-    __syncthreads();
-    for (uint32_t r = r0 + warp; r < r1; r += 8) {
-      const u64 *list = cand + (((size_t)r * n_qt + qt) * 128 + rl) * cap;
-      const uint32_t n = s_cnt[r];
-      for (uint32_t j = lane; j < n; j += 32) {
-        const u64 key = __ldcg(list + j);
-        if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+    __syncthreads();  // (cnt, thr) snapshot taken by everybody before anybody pushes
+    u64 keys[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t f = f0 + tid + u * 256;
+      keys[u] = 0ull;
+      if (f < f0 + len) {
+        uint32_t lo = 0, hi = n_ranges;  // s_pre[lo] <= f < s_pre[hi]
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (s_pre[mid] <= f) lo = mid; else hi = mid;
+        }
+        keys[u] = __ldcg(cand + (((size_t)lo * n_qt + qt) * 128 + rl) * cap + (f - s_pre[lo]));
       }
     }
-    r0 = r1;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool pass = keys[u] > thr;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&S.cnt, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (pass) S.buf[base + __popc(m & ((1u << lane) - 1))] = keys[u];
+      }
+    }
+    f0 += len;
     __syncthreads();
-    if (S.cnt > OI_SEL_CAP / 2 || r0 >= n_ranges) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
+    if (S.cnt > OI_SEL_CAP / 2 || f0 >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
   }
-  if (n_ranges == 0) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
   for (uint32_t i = tid; i < k; i += 256) out[(size_t)q * k + i] = i < S.cnt ? S.buf[i] : 0ull;
-  if (thr_out && tid == 0) thr_out[q] = S.cnt == k ? S.buf[k - 1] : 0ull;
+  if (thr_out && tid == 0) thr_out[q] = (S.cnt == k) ? S.buf[k - 1] : 0ull;
 }
 
 size_t gemm_smem_bytes() {
@@ -543,21 +599,20 @@ oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, u
   if (n_ranges < 1) n_ranges = 1;
   const uint32_t n_tiles = (uint32_t)((h->desc.n_docs + kTileDocs - 1) / kTileDocs);
   if (n_ranges > n_tiles) n_ranges = n_tiles;
-  if ((size_t)n_ranges * n_qt * 128 > g->max_lists) return h->fail(OI_ERR_CUDA, "internal: GEMM list workspace too small");
+  if (n_ranges > kMergeMaxLists || (size_t)n_ranges * n_qt * 128 > g->max_lists) return h->fail(OI_ERR_CUDA, "internal: GEMM list workspace too small");
   const uint32_t cap = h->gemm_cap ? (uint32_t)h->gemm_cap : g->cap;
   const uint32_t rows = n_qt * 128;
   {
-    const size_t n = (size_t)rows * h->desc.dim;
+    const size_t n = (size_t)rows * h->desc.dim / 2;
     unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)h->num_sms * 8);
-    gemm_prep_queries_kernel<<<blocks, 256, 0, st>>>(d_queries, nq, rows, h->desc.dim, g->d_qb);
+    gemm_prep_queries_kernel<<<blocks, 256, 0, st>>>(d_queries, nq, rows, h->desc.dim, reinterpret_cast<uint32_t *>(g->d_qb));
     ++h->launches;
     GM_CK(cudaGetLastError());
   }
-  // Passes of geometrically growing size.  The first covers as many tiles per CTA as fit a candidate list
-  // without compaction and runs without thresholds; each later pass starts from the exact k-th best key of
+  // Passes of geometrically growing size (1, 8, 64, ... tiles per CTA).  The first runs without thresholds
+  // and keeps every score, so it is kept short; each later pass starts from the exact k-th best key of
   // everything scored so far, so the share of tiles in which any score passes the filter keeps shrinking.
-  uint32_t per_range = (cap - kTileDocs) / kTileDocs;
-  if (h->gemm_sample_tiles > 0) per_range = std::min<uint32_t>(per_range, (uint32_t)h->gemm_sample_tiles);
+  uint32_t per_range = h->gemm_sample_tiles > 0 ? std::min<uint32_t>((cap - kTileDocs) / kTileDocs, (uint32_t)h->gemm_sample_tiles) : 1u;
   uint32_t done = 0;
   const u64 *prev = nullptr;
   u64 *bufs[2] = {g->d_keys_a, g->d_keys_b};
