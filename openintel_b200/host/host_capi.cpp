@@ -1,0 +1,61 @@
+// host_capi.cpp — extern "C" shim over the header-only host layer so that the CPU test-suite can
+// drive the tokenizer and the index builder (libopenintel_host.so; no CUDA in here).
+#include "openintel_host.hpp"
+
+using openintel::IndexBuilder;
+
+extern "C" {
+
+void *oih_builder_create() { return new IndexBuilder(); }
+void oih_builder_destroy(void *b) { delete static_cast<IndexBuilder *>(b); }
+
+// posts i = texts[offsets[i] .. offsets[i+1])
+void oih_builder_add(void *b, const uint8_t *texts, const uint64_t *offsets, uint64_t n_posts) {
+  IndexBuilder *ix = static_cast<IndexBuilder *>(b);
+  for (uint64_t i = 0; i < n_posts; ++i)
+    ix->add(std::string_view(reinterpret_cast<const char *>(texts) + offsets[i], offsets[i + 1] - offsets[i]));
+}
+void oih_builder_finish(void *b, uint32_t *n_docs, uint32_t *n_terms, uint64_t *n_postings) {
+  IndexBuilder *ix = static_cast<IndexBuilder *>(b);
+  ix->finish();
+  *n_docs = ix->n_docs();
+  *n_terms = ix->n_terms();
+  *n_postings = ix->doc_ids().size();
+}
+void oih_builder_export(void *b, uint64_t *term_offsets, uint32_t *doc_ids, uint32_t *tfs, uint32_t *doc_len) {
+  IndexBuilder *ix = static_cast<IndexBuilder *>(b);
+  ix->finish();
+  std::memcpy(term_offsets, ix->term_offsets().data(), ix->term_offsets().size() * sizeof(uint64_t));
+  if (!ix->doc_ids().empty()) {
+    std::memcpy(doc_ids, ix->doc_ids().data(), ix->doc_ids().size() * sizeof(uint32_t));
+    std::memcpy(tfs, ix->tfs().data(), ix->tfs().size() * sizeof(uint32_t));
+  }
+  if (ix->n_docs()) std::memcpy(doc_len, ix->doc_len().data(), (size_t)ix->n_docs() * sizeof(uint32_t));
+}
+uint32_t oih_builder_term_id(void *b, const uint8_t *tok, uint32_t len) {
+  return static_cast<IndexBuilder *>(b)->term_id(std::string_view(reinterpret_cast<const char *>(tok), len));
+}
+// returns the number of term ids the query text maps to (only the first `cap` are written)
+uint32_t oih_builder_query_terms(void *b, const uint8_t *text, uint32_t len, uint32_t *out, uint32_t cap) {
+  const std::vector<uint32_t> t = static_cast<IndexBuilder *>(b)->query_terms(std::string_view(reinterpret_cast<const char *>(text), len));
+  for (uint32_t i = 0; i < t.size() && i < cap; ++i) out[i] = t[i];
+  return (uint32_t)t.size();
+}
+// vocabulary entry `id` -> bytes; returns its length (only the first `cap` bytes are written)
+uint32_t oih_builder_term(void *b, uint32_t id, uint8_t *out, uint32_t cap) {
+  const std::string &s = static_cast<IndexBuilder *>(b)->vocabulary().at(id);
+  std::memcpy(out, s.data(), std::min<size_t>(cap, s.size()));
+  return (uint32_t)s.size();
+}
+// tokens joined by '\n'; returns the joined length (only the first `cap` bytes are written)
+uint64_t oih_tokenize(const uint8_t *text, uint64_t len, uint8_t *out, uint64_t cap) {
+  std::string joined;
+  openintel::tokenize(std::string_view(reinterpret_cast<const char *>(text), len), [&](std::string_view t) {
+    if (!joined.empty()) joined.push_back('\n');
+    joined.append(t);
+  });
+  std::memcpy(out, joined.data(), std::min<uint64_t>(cap, joined.size()));
+  return joined.size();
+}
+
+}  // extern "C"

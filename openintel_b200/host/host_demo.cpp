@@ -1,0 +1,74 @@
+// host_demo.cpp — end-to-end use of the C++ host layer: posts + embeddings in, hybrid hits out.
+//   host_demo <posts.txt> <embeddings.f32> <dim> <queries.txt> <query_embeddings.f32> <k>
+// posts.txt / queries.txt: one text per line.  Prints one line per hit: "q rank doc_id rrf rc rb",
+// then one line per post "signal i polarity speculative" from the GPU PostAnalyzer.
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+#include "openintel_host.hpp"
+
+using namespace openintel;
+
+static std::vector<std::string> read_lines(const char *path) {
+  std::ifstream f(path);
+  std::vector<std::string> out;
+  for (std::string line; std::getline(f, line);) out.push_back(line);
+  return out;
+}
+static std::vector<float> read_f32(const char *path) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  const std::streamsize n = f.tellg();
+  f.seekg(0);
+  std::vector<float> v((size_t)n / sizeof(float));
+  f.read(reinterpret_cast<char *>(v.data()), n);
+  return v;
+}
+
+int main(int argc, char **argv) {
+  if (argc != 7) { std::fprintf(stderr, "usage: host_demo posts.txt emb.f32 dim queries.txt qemb.f32 k\n"); return 2; }
+  try {
+    const std::vector<std::string> texts = read_lines(argv[1]);
+    const std::vector<float> emb = read_f32(argv[2]);
+    const uint32_t dim = (uint32_t)std::stoul(argv[3]);
+    const std::vector<std::string> qtexts = read_lines(argv[4]);
+    const std::vector<float> qemb = read_f32(argv[5]);
+    const size_t k = std::stoul(argv[6]);
+    if (emb.size() != texts.size() * dim || qemb.size() != qtexts.size() * dim) throw std::runtime_error("embedding file size mismatch");
+
+    IndexBuilder ix;
+    std::vector<SocialPost> posts;
+    for (size_t i = 0; i < texts.size(); ++i) {
+      SocialPost p;
+      p.id = "post-" + std::to_string(i);
+      p.source = "reddit";
+      p.text = texts[i];
+      posts.push_back(p);
+      ix.add(p);
+    }
+    GpuHybridSearch search(0, dim, OI_DTYPE_F32, emb.data(), ix, (uint32_t)k, (uint32_t)std::max<size_t>(qtexts.size(), 1));
+    std::vector<SearchQuery> queries;
+    for (size_t j = 0; j < qtexts.size(); ++j) {
+      SearchQuery q;
+      q.embedding.assign(qemb.begin() + j * dim, qemb.begin() + (j + 1) * dim);
+      q.terms = ix.query_terms(qtexts[j]);
+      queries.push_back(std::move(q));
+    }
+    const HybridSearch &port = search;  // callers hold the port, not the adapter
+    const auto hits = port.search(queries, k);
+    for (size_t j = 0; j < hits.size(); ++j)
+      for (size_t i = 0; i < hits[j].size(); ++i)
+        std::printf("hit %zu %zu %u %.9g %u %u\n", j, i, hits[j][i].doc_id, hits[j][i].rrf, hits[j][i].rank_cosine, hits[j][i].rank_bm25);
+    GpuLexiconAnalyzer analyzer(0);
+    const PostAnalyzer &aport = analyzer;
+    const auto sig = aport.analyze(posts);
+    for (size_t i = 0; i < sig.size(); ++i) std::printf("signal %zu %.17g %d\n", i, sig[i].polarity, sig[i].speculative ? 1 : 0);
+  } catch (const DomainError &e) {
+    std::fprintf(stderr, "DomainError(%d): %s\n", (int)e.kind, e.what());
+    return 1;
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
