@@ -6,7 +6,8 @@
 
 Workload (BASELINE.json configs[1]): 1,000,000 docs x 384-dim f32 unit rows, cosine top-100,
 single-query GEMV path.  A *step* submits QUERIES_PER_STEP independent single-query scans in one
-C-ABI call (each query is its own full pass over the matrix: one scan kernel launch per query).
+C-ABI call (each query is its own full pass over the matrix; one persistent launch walks them back
+to back).  `latency_us_nq1` is the same path called with ONE query per call.
 N > 1: the same fixed corpus is sharded by document over the N GPUs (strong scaling); every rank
 scans its shard, local top-k lists are all-gathered with NCCL and merged on device.
 
@@ -29,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_DOCS, DIM, TOPK = 1_000_000, 384, 100
-QUERIES_PER_STEP = 16
+QUERIES_PER_STEP = 64
 SEED = 20261018
 METRIC = "cosine top-100 queries/sec (single-query GEMV path, 1M x 384 f32)"
 UNIT = "queries/s"
@@ -122,7 +123,9 @@ def _synth_rows_parallel(O, n, dim, threads):
 def _traffic(key):
     """dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture"""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]["traffic_bytes_per_launch"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        # the capture was one launch of `queries_per_launch` queries; a bench launch walks QUERIES_PER_STEP
+        return t["traffic_bytes_per_launch"] / t["queries_per_launch"] * QUERIES_PER_STEP
     except Exception:
         return None
 
@@ -148,6 +151,74 @@ def cpu_baseline_leg(rows, budget_s=12.0):
             "sample": "%d full single-query passes over the 1M x 384 f32 matrix in %.1f s, %d OpenMP threads on '%s' "
                       "(self-written CPU oracle; no reference implementation of this path exists)" % (n, dt, threads, _cpu_model()),
             "gbs": n * N_DOCS * DIM * 4 / dt / 1e9}
+
+
+def _dev_time(fn, steps, warmup):
+    import torch
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def secondary_workloads(dev):
+    """The other single-GPU configurations of BASELINE.json, measured in the same run (device-timed,
+    inputs resident in HBM).  Informational: the headline line above stays configs[1]."""
+    import numpy as np
+    import torch
+    import openintel_b200 as oi
+    import oracle as O
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    # configs[3]: 10M x 768 bf16, batch 256, cosine top-100 on the tcgen05 path
+    try:
+        n, dim, nb = 10_000_000, 768, 256
+        ix = oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=TOPK, max_batch=nb)
+        ix.synth_embeddings(SEED)
+        g = torch.Generator().manual_seed(7)
+        qv = torch.randn(4, nb, dim, generator=g)
+        qv = (qv / qv.norm(dim=2, keepdim=True)).to(dev)
+        ids = torch.empty(nb, TOPK, dtype=torch.int32, device=dev)
+        sc = torch.empty(nb, TOPK, dtype=torch.float32, device=dev)
+        ms = _dev_time(lambda i: ix.search_cosine_dev(qv[i % 4], nb, TOPK, ids, sc, stream), 20, 3)
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tf = 2.0 * n * dim * nb / (ms * 1e-3) / 1e12
+        out["configs[3] cosine 10M x 768 bf16 batch 256 (tcgen05)"] = {
+            "queries_per_s": nb / (ms * 1e-3), "ms_per_batch": ms, "tensor_tflops": tf, "hbm_gbs": n * dim * 2 / (ms * 1e-3) / 1e9,
+            "frac_of_measured_bf16_sustained": tf / peaks["bf16_tflops_sustained"] if peaks else None,
+            "frac_of_measured_bf16_burst": tf / peaks["bf16_tflops"] if peaks else None}
+        ix.close()
+    except Exception as e:  # informational leg: never take the headline down
+        out["configs[3]"] = {"error": str(e)[:200]}
+    # hybrid BM25 + cosine + RRF on the configs[1] corpus (1M x 384 f32, 1M-term Zipf vocabulary), batch 16
+    try:
+        n, vocab, nb = N_DOCS, 1_000_000, 16
+        cdf = O.zipf_cdf(vocab)
+        ix = oi.GpuIndex(n_docs=n, dim=DIM, max_k=TOPK, max_batch=nb)
+        ix.synth_embeddings(SEED)
+        ix.synth_bm25(SEED, vocab, cdf)
+        ix.bm25_finalize()
+        g = torch.Generator().manual_seed(7)
+        qv = torch.randn(4, nb, DIM, generator=g)
+        qv = (qv / qv.norm(dim=2, keepdim=True)).to(dev)
+        qt = [torch.from_numpy(O.synth_query_terms(nb, 8, cdf, first=p * nb).astype(np.int32).reshape(-1)).to(dev) for p in range(4)]
+        offs = torch.arange(0, nb * 8 + 1, 8, dtype=torch.int32, device=dev)
+        o = [torch.empty(nb, TOPK, dtype=torch.int32, device=dev) for _ in range(3)]
+        rrf = torch.empty(nb, TOPK, dtype=torch.float32, device=dev)
+        ms = _dev_time(lambda i: ix.search_hybrid_dev(qv[i % 4], qt[i % 4], offs, nb, TOPK, 60, o[0], rrf, o[1], o[2], stream), 20, 3)
+        ms_b = _dev_time(lambda i: ix.search_bm25_dev(qt[i % 4], offs, nb, TOPK, o[0], rrf, stream), 20, 3)
+        out["hybrid BM25+cosine+RRF top-100, 1M x 384 f32, 1M-term Zipf vocab, batch 16"] = {
+            "queries_per_s": nb / (ms * 1e-3), "ms_per_batch": ms, "ms_bm25_only": ms_b}
+        ix.close()
+    except Exception as e:
+        out["hybrid"] = {"error": str(e)[:200]}
+    return out
 
 
 def run_reference(args, rank):
@@ -177,8 +248,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (counter-hash unit rows, seed 20261018)",
-        "config": {"workload": WORKLOAD, "queries_per_step": qper, "n_docs": N_DOCS, "dim": DIM, "k": TOPK,
-                   "note": "reference has no implementation of this path; CPU oracle port timed instead"},
+        "config": {"workload": WORKLOAD, "queries_per_step": QUERIES_PER_STEP, "n_docs": N_DOCS, "dim": DIM, "k": TOPK,
+                   "parallelism": "host cores (OpenMP)", "kernel_variant": "CPU oracle port",
+                   "note": "the reference has no implementation of this path (SURVEY.md §0); the CPU oracle port is timed; "
+                           "each step is a bounded sample: %d of the step's %d queries" % (qper, QUERIES_PER_STEP)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -193,6 +266,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=None, help="cosine kernel variant override (0 ldg, 1 bulk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the informational configs[3] / hybrid legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,6 +371,9 @@ def main():
     barrier()
     e2e_value = n_queries / e2e_s
 
+    # ---- single-query latency: one query per call, device-resident --------------------------------
+    lat_ms = _dev_time(lambda i: ix.search_cosine_dev(d_pool[i % n_pool][:1], 1, TOPK, d_ids[:1], d_sc[:1], stream), 50, 5)
+
     # ---- sanity outside the timed region: results are ranked lists of real docs -------------------
     ids = h_ids.numpy().view(np.uint32)
     sc = h_sc.numpy()
@@ -327,14 +404,18 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic("cosine_scan_bulk_f32_1Mx384_q16") if (world == 1 and not per_query_launch) else None,
-                         "traffic_source": "profiles/r01_ncu_cosine_scan_bulk.md (ncu --set full, same kernel and shape)",
+                         "traffic_source": "profiles/r01_ncu_cosine_scan_bulk.md (ncu --set full, same kernel and shape; per-query DRAM bytes x queries per launch)",
                          "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel": "cosine_scan_*_kernel", "bytes_per_launch": bytes_per_launch,
                          "avg_launch_us": avg_launch_s * 1e6,
                          "note": "avg launch = timed region / scan launches (includes unpack + launch gaps)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "latency_us_nq1": lat_ms * 1e3,
         }
+        if world == 1 and not args.no_secondary:
+            ix.close()
+            out["secondary"] = secondary_workloads(dev)
         print(json.dumps(out))
     ix.close()
     if dist is not None:
