@@ -141,6 +141,10 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->cosine_variant = (int)value;
     return OI_OK;
   }
+  if (!strcmp(name, "cosine_scan_shape")) {  // experiments: value = tile_rows * 256 + stages (0 = default)
+    oi_cosine_scan_tuning((int)(value >> 8), (int)(value & 255));
+    return OI_OK;
+  }
   if (!strcmp(name, "cosine_gemm_min_batch")) {
     OI_REQUIRE(value >= 0 && value <= 65536, "cosine_gemm_min_batch must be in 0..65536 (0 = tensor-core path off)");
     h->gemm_min_batch = (int)value;

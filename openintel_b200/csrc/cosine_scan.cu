@@ -17,6 +17,9 @@
 #include "internal.h"
 #include "oi_common.cuh"
 
+static int g_tile_rows_override = 0, g_stages_override = 0;  // tuning experiments (oi_index_set_option)
+void oi_cosine_scan_tuning(int tile_rows, int stages) { g_tile_rows_override = tile_rows; g_stages_override = stages; }
+
 namespace {
 
 constexpr int kConsumerThreads = 256;
@@ -115,21 +118,59 @@ __device__ void scan_epilogue(SelState &S, const OiScanParams &p, int tid, int n
   oi_bar_sync(bar, nthreads);
   if (tid == 0) { S.cnt = 0; S.thr = T > 0 ? T - 1 : 0; }
   oi_bar_sync(bar, nthreads);
-  // (2) stream every candidate through the filter + buffer
-  const uint32_t total = G * k;
-  uint32_t base = 0;
-  while (base < total) {
-    // snapshot (cnt, thr) before anybody pushes: loop bounds must be CTA-uniform
-    const uint32_t span = min(total - base, (uint32_t)OI_SEL_CAP - S.cnt);
-    const u64 thr = S.thr;
-    oi_bar_sync(bar, nthreads);
-    for (uint32_t i = base + tid; i < base + span; i += nthreads) {
-      u64 key = __ldcg(p.cand + i);
-      if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+  // (2) every list is sorted, so its keys above the bound are a prefix.  Measure the prefixes (gallop +
+  //     bisect: ~3 dependent loads per list), and when they fit the buffer together copy them in place —
+  //     the common case, a few hundred keys.  One CTA does this for every query, so it must take
+  //     microseconds: it is the serial stage of the whole scan pipeline.
+  const u64 bound = S.thr;
+  uint32_t *s_n = reinterpret_cast<uint32_t *>(S.buf + OI_SEL_CAP / 2);  // [G] prefix lengths, then [G] offsets
+  uint32_t *s_off = s_n + G;
+  for (uint32_t c = tid; c < G; c += nthreads) {
+    const u64 *list = p.cand + (size_t)c * k;
+    uint32_t lo = 0, hi = 1;  // keys [0, lo) pass; find the first position that does not
+    while (hi <= k && __ldcg(list + hi - 1) > bound) { lo = hi; hi <<= 1; }
+    hi = min(hi - 1, k);      // position hi (if < k) fails or is the end
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldcg(list + mid) > bound) lo = mid + 1; else hi = mid;
     }
-    base += span;
+    s_n[c] = lo;
+  }
+  oi_bar_sync(bar, nthreads);
+  if (tid == 0) {
+    uint32_t sum = 0;
+    for (uint32_t c = 0; c < G; ++c) { s_off[c] = sum; sum += s_n[c]; }
+    S.is_last = sum;  // reused as the broadcast slot for the total
+  }
+  oi_bar_sync(bar, nthreads);
+  const uint32_t total_pass = S.is_last;
+  if (total_pass <= OI_SEL_CAP / 2) {
+    for (uint32_t c = tid; c < G; c += nthreads) {
+      const u64 *list = p.cand + (size_t)c * k;
+      const uint32_t n = s_n[c], o = s_off[c];
+      for (uint32_t i = 0; i < n; ++i) S.buf[o + i] = __ldcg(list + i);
+    }
     oi_bar_sync(bar, nthreads);
-    if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
+    if (tid == 0) S.cnt = total_pass;
+    oi_bar_sync(bar, nthreads);
+    oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
+  } else {
+    // many keys above the bound (heavy ties / skewed lists): stream everything through the filter + buffer
+    const uint32_t total = G * k;
+    uint32_t base = 0;
+    while (base < total) {
+      // snapshot (cnt, thr) before anybody pushes: loop bounds must be CTA-uniform
+      const uint32_t span = min(total - base, (uint32_t)OI_SEL_CAP - S.cnt);
+      const u64 thr = S.thr;
+      oi_bar_sync(bar, nthreads);
+      for (uint32_t i = base + tid; i < base + span; i += nthreads) {
+        u64 key = __ldcg(p.cand + i);
+        if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+      }
+      base += span;
+      oi_bar_sync(bar, nthreads);
+      if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
+    }
   }
   // (3) emit and re-arm the per-query control words for the next launch
   for (uint32_t i = tid; i < k; i += nthreads) p.out_keys[i] = i < S.cnt ? S.buf[i] : 0ull;
@@ -267,14 +308,19 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_generic_kerne
 // =================================================================================================
 constexpr uint32_t kTileEnd = 0xFFFFFFFFu;
 constexpr int kBulkWarps = 16;                  // consumer warps of the bulk variant
-constexpr int kBulkThreads = kBulkWarps * 32;   // + one producer warp
+constexpr int kBulkThreads = kBulkWarps * 32;   // + one producer warp + the epilogue warps
+constexpr int kEpiWarps = 4;                    // run a query's list merge while the consumers scan the next query
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kBulkBlock = kBulkThreads + 32 + kEpiThreads;
 
 template <typename T, int NVL, bool EXACT>
-__global__ void __launch_bounds__(kBulkThreads + 32, 1)
+__global__ void __launch_bounds__(kBulkBlock, 1)
     cosine_scan_bulk_kernel(const OiScanParams p, const uint32_t tile_rows, const uint32_t n_stages) {
   constexpr int QF = Elem<T>::QF;
   extern __shared__ __align__(128) unsigned char s_dyn[];
-  __shared__ SelState S;
+  // two selection states: query i fills slot i & 1 while the epilogue warps finish query i - 1 in the other
+  __shared__ SelState S2[2];
+  __shared__ u64 s_qdone[2], s_edone[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t row_bytes = p.nv * 16u;
   const uint32_t tile_bytes = tile_rows * row_bytes;
@@ -285,10 +331,34 @@ __global__ void __launch_bounds__(kBulkThreads + 32, 1)
 
   if (tid == 0) {
     for (uint32_t s = 0; s < n_stages; ++s) { oi_mbar_init(&full[s], 1); oi_mbar_init(&empty[s], kBulkWarps); }
+    for (int b = 0; b < 2; ++b) { oi_mbar_init(&s_qdone[b], 1); oi_mbar_init(&s_edone[b], 1); S2[b].cnt = 0; S2[b].thr = 0ull; }
     oi_mbar_fence_init();
-    S.cnt = 0; S.thr = 0ull;
   }
   __syncthreads();
+
+  if (warp > kBulkWarps) {
+    // ---------------- epilogue warps: publish + (last CTA) merge the lists of query qi -----------------
+    const int etid = tid - (kBulkThreads + 32);
+    for (uint32_t qi = 0; qi < p.nq; ++qi) {
+      const uint32_t slot = qi & 1u, ph = (qi >> 1) & 1u;
+      SelState &S = S2[slot];
+      OiScanParams pq = p;
+      pq.cand = p.cand + (size_t)qi * p.cand_stride;
+      pq.gthr = p.gthr + qi;
+      pq.ticket = p.ticket + qi;
+      pq.tile_ctr = p.tile_ctr + qi;
+      pq.out_keys = p.out_keys + (size_t)qi * p.k;
+      oi_mbar_wait(&s_qdone[slot], ph);
+      scan_epilogue(S, pq, etid, kEpiThreads, 2);
+      oi_bar_sync(2, kEpiThreads);
+      if (etid == 0) {
+        S.cnt = 0; S.thr = 0ull;
+        __threadfence_block();
+        oi_mbar_arrive(&s_edone[slot]);
+      }
+    }
+    return;
+  }
 
   if (warp == kBulkWarps) {
     // ---------------- producer: one elected lane, all queries of the batch back to back ----------
@@ -324,13 +394,13 @@ __global__ void __launch_bounds__(kBulkThreads + 32, 1)
   // -------------------------------- consumers --------------------------------------------------
   uint32_t it = 0;
   for (uint32_t qi = 0; qi < p.nq; ++qi) {
+    const uint32_t slot = qi & 1u;
+    SelState &S = S2[slot];
     OiScanParams pq = p;
     pq.q = p.q + (size_t)qi * p.dim;
-    pq.cand = p.cand + (size_t)qi * p.cand_stride;
     pq.gthr = p.gthr + qi;
-    pq.ticket = p.ticket + qi;
-    pq.tile_ctr = p.tile_ctr + qi;
-    pq.out_keys = p.out_keys + (size_t)qi * p.k;
+    // the slot is free once the epilogue of query qi - 2 has re-armed it
+    oi_mbar_wait(&s_edone[slot], ((qi >> 1) & 1u) ^ 1u);
     float q[NVL][QF];
 #pragma unroll
     for (int j = 0; j < NVL; ++j) {
@@ -402,12 +472,12 @@ __global__ void __launch_bounds__(kBulkThreads + 32, 1)
         if (tid == 0 && S.cnt == p.k) atomicMax(pq.gthr, S.thr);
       }
     }
-    // this query is done in this CTA: publish its list (the last CTA to arrive merges) while the
-    // producer already streams the next query's tiles into the ring
-    scan_epilogue(S, pq, tid, kBulkThreads, 1);
-    oi_bar_sync(1, kBulkThreads);
-    if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
-    oi_bar_sync(1, kBulkThreads);
+    // this query is done in this CTA: hand its candidates to the epilogue warps (final compaction, publish, and
+    // in the last CTA to arrive the merge of all lists) and start on the next query's tiles right away
+    if (tid == 0) {
+      __threadfence_block();
+      oi_mbar_arrive(&s_qdone[slot]);
+    }
   }
 }
 
@@ -441,12 +511,18 @@ cudaError_t dispatch_ldg(const OiScanParams &p, uint32_t grid, cudaStream_t st) 
   }
 }
 
-// tile = a multiple of 32 rows (2 rows x 16 consumer warps) of at most 48 KB (16 rows for very wide rows); ring of <= 8 stages in 200 KB
+// tile = a multiple of 32 rows (2 rows x 16 consumer warps) of at most 48 KB (16 rows for very wide rows); ring of <= 8 stages in 176 KB
 static inline void bulk_tile_shape(uint32_t row_bytes, uint32_t *tile_rows, uint32_t *n_stages) {
+  if (g_tile_rows_override > 0 && g_stages_override >= 2 &&
+      (size_t)g_tile_rows_override * row_bytes * g_stages_override <= 176u * 1024u && g_tile_rows_override % 32 == 0) {
+    *tile_rows = (uint32_t)g_tile_rows_override;
+    *n_stages = (uint32_t)g_stages_override;
+    return;
+  }
   uint32_t tr = (49152u / row_bytes) & ~31u;
   if (tr < 16) tr = 16;
   if (tr > 256) tr = 256;
-  uint32_t ns = (uint32_t)((200u * 1024u) / (tr * row_bytes));
+  uint32_t ns = (uint32_t)((176u * 1024u) / (tr * row_bytes));  // + 2 x 16.4 KB selection states <= 227 KB
   if (ns > 8) ns = 8;
   *tile_rows = tr;
   *n_stages = ns;
@@ -463,8 +539,8 @@ cudaError_t launch_bulk(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
   cudaError_t e = exact ? cudaFuncSetAttribute(cosine_scan_bulk_kernel<T, NVL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                         : cudaFuncSetAttribute(cosine_scan_bulk_kernel<T, NVL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (exact) cosine_scan_bulk_kernel<T, NVL, true><<<grid, kBulkThreads + 32, smem, st>>>(p, tile_rows, n_stages);
-  else cosine_scan_bulk_kernel<T, NVL, false><<<grid, kBulkThreads + 32, smem, st>>>(p, tile_rows, n_stages);
+  if (exact) cosine_scan_bulk_kernel<T, NVL, true><<<grid, kBulkBlock, smem, st>>>(p, tile_rows, n_stages);
+  else cosine_scan_bulk_kernel<T, NVL, false><<<grid, kBulkBlock, smem, st>>>(p, tile_rows, n_stages);
   return cudaGetLastError();
 }
 

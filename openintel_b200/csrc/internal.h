@@ -49,6 +49,7 @@ cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_
                                   const OiCosineWorkspace &ws, u64 *d_out_keys, int variant, int num_sms,
                                   cudaStream_t stream, uint64_t *launches);
 uint32_t oi_cosine_scan_max_grid(int num_sms);
+void oi_cosine_scan_tuning(int tile_rows, int stages);  // experiments: 0 = default shape
 
 // keys -> (ids, scores) / (ids, rrf ...) unpack; merge of gathered shard lists -----------------
 cudaError_t oi_launch_unpack_keys(const u64 *d_keys, uint32_t n, uint32_t *d_ids, float *d_scores,

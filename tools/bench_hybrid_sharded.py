@@ -1,0 +1,111 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs[4]: full hybrid (BM25 + cosine + RRF top-100) over a document-sharded corpus,
+one process per GPU, NCCL all-gather of the local top-k lists + device merge (SPEC §5).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/bench_hybrid_sharded.py [--docs 100000000 --dim 768 --vocab 1000000 --batch 256]
+
+Strong scaling: the corpus is fixed, every rank holds docs/N of it (the embeddings of the default
+corpus are 153.6 GB bf16, so N >= 2).  Rank 0 prints one JSON line; time = max over ranks, CUDA events."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SEED = 20261018
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--docs", type=int, default=100_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-bm25", action="store_true")
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import openintel_b200 as oi
+    from openintel_b200 import sharding
+    import oracle as O
+
+    rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    d = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        d = dist
+    cdf = O.zipf_cdf(a.vocab)
+    t0 = time.perf_counter()
+    sh = sharding.ShardedIndex(a.docs, a.dim, dtype=oi.DTYPE_BF16, dist=d, device_index=lr, max_k=a.k, max_batch=a.batch)
+    sh.ix.synth_embeddings(SEED)
+    if not a.no_bm25:
+        sh.ix.synth_bm25(SEED, a.vocab, cdf)
+        sh.finalize_bm25()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    ix = sh.ix
+    g = torch.Generator().manual_seed(7)
+    qv = torch.randn(4, a.batch, a.dim, generator=g)
+    qv = (qv / qv.norm(dim=2, keepdim=True)).to(dev)
+    qt = [torch.from_numpy(O.synth_query_terms(a.batch, 8, cdf, first=p * a.batch).astype(np.int32).reshape(-1)).to(dev) for p in range(4)]
+    offs = torch.arange(0, a.batch * 8 + 1, 8, dtype=torch.int32, device=dev)
+    o = [torch.empty(a.batch, a.k, dtype=torch.int32, device=dev) for _ in range(3)]
+    rrf = torch.empty(a.batch, a.k, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def timed(fn):
+        for i in range(a.warmup):
+            fn(i)
+        if d is not None:
+            d.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            fn(a.warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        if d is not None:
+            t = torch.tensor([ms], device=dev)
+            d.all_reduce(t, op=d.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ms_cos = timed(lambda i: ix.search_cosine_dev(qv[i % 4], a.batch, a.k, o[0], rrf, stream))
+    res = {"workload": "configs[4]: hybrid BM25+cosine+RRF top-%d, %d docs x %d bf16 sharded over %d GPU(s), %d-term Zipf vocab, batch %d"
+                       % (a.k, a.docs, a.dim, world, a.vocab, a.batch),
+           "n_gpus": world, "docs_per_gpu": sh.n_local, "unit": "queries/s", "scaling": "strong", "build_s": build_s,
+           "ms_cosine_only": ms_cos, "cosine_queries_per_s": a.batch / (ms_cos * 1e-3),
+           "cosine_hbm_GBps_per_gpu": sh.n_local * a.dim * 2 / (ms_cos * 1e-3) / 1e9,
+           "cosine_tensor_TFLOPs_per_gpu": 2.0 * sh.n_local * a.dim * a.batch / (ms_cos * 1e-3) / 1e12}
+    if not a.no_bm25:
+        ms_bm = timed(lambda i: ix.search_bm25_dev(qt[i % 4], offs, a.batch, a.k, o[0], rrf, stream))
+        ms = timed(lambda i: ix.search_hybrid_dev(qv[i % 4], qt[i % 4], offs, a.batch, a.k, 60, o[0], rrf, o[1], o[2], stream))
+        res.update({"value": a.batch / (ms * 1e-3), "ms_per_batch": ms, "ms_bm25_only": ms_bm})
+    # sanity: ranked lists of real docs, identical on every rank
+    ids = o[0].cpu().numpy().view(np.uint32)
+    assert ids[ids != 0xFFFFFFFF].max() < a.docs
+    if d is not None:
+        ref = o[0].clone()
+        d.broadcast(ref, 0)
+        assert torch.equal(ref, o[0]), "ranks disagree on the merged lists"
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    sh.close()
+    if d is not None:
+        d.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
