@@ -25,7 +25,9 @@
 //   algorithmic bytes per query = postings touched x 8 B (doc id + folded weight)
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cmath>
+#include <utility>
 #include <vector>
 
 #include "../../include/oi_synth_tables.h"
@@ -35,8 +37,6 @@
 
 #define OI_BM25_MAX_QTERMS 64
 #define OI_BM25_ACC_FLOATS 32768  // 128 KB of block scores per CTA, split over the CTA's groups
-#define OI_BM25_THREADS 512
-#define OI_BM25_CHUNK 128         // postings per warp per step (4 x 32 lanes)
 
 struct OiBm25 {
   uint32_t n_terms = 0;
@@ -45,7 +45,11 @@ struct OiBm25 {
   uint32_t *d_doc_ids = nullptr;  // [P] shard-local doc ids, ascending inside a list
   uint32_t *d_tfs = nullptr;      // [P]
   uint32_t *d_doc_len = nullptr;  // [n_docs]
-  float *d_w = nullptr;           // [P] folded weights (after finalize)
+  float *d_w = nullptr;           // [P] folded weights (after finalize; export)
+  uint2 *d_post = nullptr;        // [P + 2] interleaved (doc id, weight bits): what the scoring kernel streams
+  float *d_dense = nullptr;       // [n_dense][dense_stride] weight columns of the densest terms
+  int *d_dense_slot = nullptr;    // [n_terms] column index or -1
+  uint32_t n_dense = 0, dense_stride = 0;
   bool finalized = false;
   // search workspace
   uint32_t *d_qterms = nullptr;   // [max_batch][64] sorted distinct valid terms
@@ -118,108 +122,110 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
   return v;
 }
 
+#define OI_BM25_NONE 0xFFFFFFFFu
+#define OI_BM25_MAX_DENSE 16
+
 struct Bm25Params {
   const u64 *term_off;
   const uint32_t *doc_ids;
-  const float *w;
-  const uint32_t *qterms;  // [nq][64]
-  const uint32_t *qnt;     // [nq]
-  u64 *gthr;               // [nq]
+  const uint2 *post;          // [P + 2] interleaved (doc id, folded weight bits)
+  const float *dense;         // [n_dense][dense_stride] weight columns of the densest terms (0 where absent)
+  const int *dense_slot;      // [n_terms] column of a term, or -1
+  uint32_t dense_stride;
+  const uint32_t *qterms;     // [nq][64]
+  const uint32_t *qnt;        // [nq]
+  u64 *gthr;                  // [nq]
   uint32_t *counter;
-  u64 *lists;              // [S][nq][k]
+  u64 *lists;                 // [S][nq][k]
   uint32_t n_docs, doc_base, nq, k;
-  uint32_t cap;            // candidate buffer keys per group (power of two, >= 2k)
-  uint32_t R;              // docs per block
-  uint32_t J;              // blocks per super-range
-  uint32_t S;              // super-ranges
+  uint32_t cap;               // candidate buffer keys per warp (power of two, >= 2k)
+  uint32_t R;                 // docs per block
+  uint32_t J;                 // blocks per super-range
+  uint32_t S;                 // super-ranges
   uint32_t n_blocks;
-  uint32_t group_size;     // threads per group
+  uint32_t ng;                // warps (= work items in flight) per CTA
 };
 
-// One warp applies its share of term postings [pos, e) that fall below doc id `bend`.
-// Chunks of 128 postings are dealt round-robin to the `n_warps` warps of the group (warp `wg`
-// takes chunks wg, wg + n_warps, ...).  Returns the number of in-block postings this warp applied;
-// *first_out = the doc id of the first posting this warp saw that is NOT in the block
-// (0xFFFFFFFF when its share of the list is exhausted).
-__device__ __forceinline__ uint32_t walk_term(const uint32_t *__restrict__ dids, const float *__restrict__ ws,
-                                              uint32_t pos, uint32_t e, uint32_t bbase, uint32_t bend,
-                                              float *acc, int wg, int n_warps, int lane, uint32_t *first_out) {
-  uint32_t total = 0;
-  uint32_t c = pos + (uint32_t)wg * OI_BM25_CHUNK;
-  uint32_t d[4];
-  float w[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t p = c + 32 * j + lane;
-    const bool ok = p < e;
-    d[j] = ok ? __ldg(dids + p) : 0xFFFFFFFFu;
-    w[j] = ok ? __ldg(ws + p) : 0.0f;
-  }
-  for (;;) {
-    // the chunk is entirely inside the block iff its last posting is
-    const bool full = __shfl_sync(0xFFFFFFFFu, d[3], 31) < bend;
-    if (full) {
-      const uint32_t cn = c + (uint32_t)n_warps * OI_BM25_CHUNK;
-      uint32_t d2[4];
-      float w2[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {  // prefetch this warp's next chunk before touching shared memory
-        const uint32_t p = cn + 32 * j + lane;
-        const bool ok = p < e;
-        d2[j] = ok ? __ldg(dids + p) : 0xFFFFFFFFu;
-        w2[j] = ok ? __ldg(ws + p) : 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float *a = acc + (d[j] - bbase);
-        *a = *a + w[j];  // SPEC §3: one f32 add, previous terms first
-      }
-      total += OI_BM25_CHUNK;
-      c = cn;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { d[j] = d2[j]; w[j] = w2[j]; }
-    } else {
-      uint32_t n = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool in = d[j] < bend;
-        if (in) {
-          float *a = acc + (d[j] - bbase);
-          *a = *a + w[j];
-        }
-        n += __popc(__ballot_sync(0xFFFFFFFFu, in));
-      }
-      total += n;
-      // n < 128 here: posting n of the chunk is the first one outside the block
-      const uint32_t jn = n >> 5;
-      const uint32_t dj = jn == 0 ? d[0] : jn == 1 ? d[1] : jn == 2 ? d[2] : d[3];
-      *first_out = __shfl_sync(0xFFFFFFFFu, dj, n & 31);
-      break;
-    }
-  }
-  return total;
+__device__ __forceinline__ uint4 ldg_post2(const uint2 *p) {
+  return __ldg(reinterpret_cast<const uint4 *>(p));
 }
 
-// dynamic shared memory layout (per CTA, NG = groups per CTA):
+// One term's postings inside the block [bbase, bend): the warp reads the interleaved (doc, weight) array 64
+// postings at a time (one 16-byte load = 2 postings per lane) from the 16-byte-aligned pair at or below the
+// cursor, adds every weight whose document is below `bend` to acc[], and stops at the first posting outside
+// the block.  *pos_out = the new cursor, *nxt_out = the document there (NONE at the end of the list).
+__device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 base, uint32_t pos, uint32_t end, uint32_t bbase,
+                                            uint32_t bend, float *acc, int lane, uint32_t *pos_out, uint32_t *nxt_out) {
+  const u64 g0 = base + pos, gend = base + end;
+  u64 a = g0 & ~1ull;
+  uint32_t skip = (uint32_t)(g0 - a);  // a leading slot below the cursor (0 or 1)
+  uint32_t applied = 0, nxt = OI_BM25_NONE;
+  for (;;) {
+    const u64 idx = a + 2u * (uint32_t)lane;
+    uint4 v = make_uint4(OI_BM25_NONE, 0u, OI_BM25_NONE, 0u);
+    if (idx < gend) v = ldg_post2(post + idx);   // the array is padded, so reading the pair is always in bounds
+    if (idx + 1 >= gend) v.z = OI_BM25_NONE;      // second slot belongs to the next list
+    if (idx < g0) v.x = OI_BM25_NONE;             // leading slot below the cursor: skipped, not applied
+    const bool in0 = idx >= g0 && v.x < bend, in1 = v.z < bend;
+    if (in0) {
+      float *x = acc + (v.x - bbase);
+      *x = *x + __uint_as_float(v.y);  // SPEC §3: one f32 add, previous terms first
+    }
+    if (in1) {
+      float *x = acc + (v.z - bbase);
+      *x = *x + __uint_as_float(v.w);
+    }
+    const uint32_t n = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in0)) + (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in1));
+    applied += n;
+    if (skip + n < 64u) {  // slot (skip + n) is the first posting outside the block, or past the end of the list
+      const uint32_t sl = skip + n;
+      const uint32_t d = (sl & 1u) ? v.z : v.x;
+      nxt = __shfl_sync(0xFFFFFFFFu, d, (int)(sl >> 1));
+      if (a + sl >= gend) nxt = OI_BM25_NONE;
+      break;
+    }
+    a += 64;
+    skip = 0;
+  }
+  *pos_out = pos + applied;
+  *nxt_out = nxt;
+}
+
+// A dense term: its weight column for the block is added to every document (0.0f where the term is absent,
+// which leaves a non-negative f32 sum bit-for-bit unchanged), 128-bit loads, 4 in flight per lane.
+__device__ __forceinline__ void dense_pass(const float *__restrict__ col, float *acc, uint32_t R, int lane) {
+  const float4 *c4 = reinterpret_cast<const float4 *>(col);
+  float4 *a4 = reinterpret_cast<float4 *>(acc);
+  for (uint32_t j0 = 0; j0 < R / 4; j0 += 128) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(c4 + j0 + 32 * u + lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float4 x = a4[j0 + 32 * u + lane];
+      x.x = x.x + v[u].x; x.y = x.y + v[u].y; x.z = x.z + v[u].z; x.w = x.w + v[u].w;
+      a4[j0 + 32 * u + lane] = x;
+    }
+  }
+}
+
+// dynamic shared memory layout (per CTA, NG = warps per CTA):
 //   float acc[OI_BM25_ACC_FLOATS]            NG slices of R floats
 //   u64   cand[NG][cap]
 //   u64   tbase[NG][64]      posting-array offset of each term's list
 //   u32   tcur[NG][64]       cursor inside the list (postings consumed so far)
 //   u32   tend[NG][64]       list length
-//   u32   tnxt[NG][64]       doc id at the cursor (0xFFFFFFFF = exhausted)
-//   u32   tnew[NG][64]       min-reduction slot for the next value of tnxt
+//   u32   tnxt[NG][64]       doc id at the cursor (NONE = exhausted)
+//   u32   tden[NG][64]       dense column of the term (NONE = sparse)
 //   GrpCtl ctl[NG]
-__global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const Bm25Params p) {
+__global__ void __launch_bounds__(512, 1) bm25_blocked_kernel(const Bm25Params p) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  const int GS = (int)p.group_size;
-  const int NG = OI_BM25_THREADS / GS;
-  const int gi = threadIdx.x / GS;
+  const int NG = (int)p.ng;
+  const int gi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Grp g;
-  g.tid = threadIdx.x % GS;
-  g.size = GS;
-  g.bar = 1 + gi;
-  const int lane = threadIdx.x & 31;
-  const int wg = g.tid >> 5, n_warps = GS >> 5;
+  g.tid = lane;
+  g.size = 32;
+  g.bar = 0;
 
   float *acc_all = reinterpret_cast<float *>(s_dyn);
   u64 *cand_all = reinterpret_cast<u64 *>(s_dyn + sizeof(float) * OI_BM25_ACC_FLOATS);
@@ -227,8 +233,8 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
   uint32_t *tcur_all = reinterpret_cast<uint32_t *>(tbase_all + (size_t)NG * OI_BM25_MAX_QTERMS);
   uint32_t *tend_all = tcur_all + NG * OI_BM25_MAX_QTERMS;
   uint32_t *tnxt_all = tend_all + NG * OI_BM25_MAX_QTERMS;
-  uint32_t *tnew_all = tnxt_all + NG * OI_BM25_MAX_QTERMS;
-  GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(tnew_all + NG * OI_BM25_MAX_QTERMS);
+  uint32_t *tden_all = tnxt_all + NG * OI_BM25_MAX_QTERMS;
+  GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(tden_all + NG * OI_BM25_MAX_QTERMS);
 
   const uint32_t R = p.R;
   float *acc = acc_all + (size_t)gi * R;
@@ -237,111 +243,85 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
   uint32_t *tcur = tcur_all + gi * OI_BM25_MAX_QTERMS;
   uint32_t *tend = tend_all + gi * OI_BM25_MAX_QTERMS;
   uint32_t *tnxt = tnxt_all + gi * OI_BM25_MAX_QTERMS;
-  uint32_t *tnew = tnew_all + gi * OI_BM25_MAX_QTERMS;
+  uint32_t *tden = tden_all + gi * OI_BM25_MAX_QTERMS;
   GrpCtl *ctl = ctl_all + gi;
 
-  for (uint32_t i = g.tid; i < R; i += GS) acc[i] = 0.0f;
+  for (uint32_t i = lane; i < R; i += 32) acc[i] = 0.0f;
   const uint32_t n_items = p.S * p.nq;
   const uint32_t k = p.k, cap = p.cap;
 
   for (;;) {
-    g.sync();
-    if (g.tid == 0) ctl->item = atomicAdd(p.counter, 1u);
-    g.sync();
-    const uint32_t item = ctl->item;
+    __syncwarp();
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(p.counter, 1u);
+    item = __shfl_sync(0xFFFFFFFFu, item, 0);
     if (item >= n_items) break;
     const uint32_t s = item / p.nq, q = item % p.nq;
     const uint32_t nt = p.qnt[q];
     const uint32_t blk0 = s * p.J, blk1 = min(p.n_blocks, blk0 + p.J);
     const uint32_t doc0 = blk0 * R;
 
-    // ---- item set-up: one binary search per term positions the cursor at the super-range start
-    for (uint32_t i = g.tid; i < nt; i += GS) {
+    // ---- item set-up: one binary search per sparse term positions the cursor at the super-range start
+    for (uint32_t i = lane; i < nt; i += 32) {
       const uint32_t t = p.qterms[(size_t)q * OI_BM25_MAX_QTERMS + i];
       const u64 lo = p.term_off[t], hi = p.term_off[t + 1];
-      u64 a = lo, b = hi;
-      while (a < b) {
-        const u64 mid = a + ((b - a) >> 1);
-        if (__ldg(p.doc_ids + mid) < doc0) a = mid + 1; else b = mid;
-      }
+      const int slot = p.dense_slot[t];
       tbase[i] = lo;
-      tcur[i] = (uint32_t)(a - lo);
       tend[i] = (uint32_t)(hi - lo);
-      tnxt[i] = a < hi ? __ldg(p.doc_ids + a) : 0xFFFFFFFFu;
-      tnew[i] = 0xFFFFFFFFu;
+      if (slot >= 0) {  // dense terms touch every block
+        tden[i] = (uint32_t)slot;
+        tcur[i] = 0;
+        tnxt[i] = doc0;
+      } else {
+        u64 a = lo, b = hi;
+        while (a < b) {
+          const u64 mid = a + ((b - a) >> 1);
+          if (__ldg(p.doc_ids + mid) < doc0) a = mid + 1; else b = mid;
+        }
+        tden[i] = OI_BM25_NONE;
+        tcur[i] = (uint32_t)(a - lo);
+        tnxt[i] = a < hi ? __ldg(p.doc_ids + a) : OI_BM25_NONE;
+      }
     }
-    if (g.tid == 0) { ctl->cnt = 0; ctl->thr = 0ull; ctl->aux = 0; }
-    g.sync();
+    if (lane == 0) { ctl->cnt = 0; ctl->thr = 0ull; ctl->aux = 0; }
+    __syncwarp();
 
     uint32_t blk = blk0;
     while (blk < blk1) {
       // ---- skip straight to the next block that holds a posting of any query term -------------
-      uint32_t mn = 0xFFFFFFFFu;
-      for (uint32_t i = 0; i < nt; ++i) mn = min(mn, tnxt[i]);  // group-uniform (shared memory)
-      if (mn == 0xFFFFFFFFu) break;
+      uint32_t mn = OI_BM25_NONE;
+      for (uint32_t i = lane; i < nt; i += 32) mn = min(mn, tnxt[i]);
+      mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+      if (mn == OI_BM25_NONE) break;
       blk = max(blk, mn / R);
       if (blk >= blk1) break;
       const uint32_t bbase = blk * R;
       const uint32_t bend = min(p.n_docs, bbase + R);
       ++blk;
-      // ---- term passes, ascending term id; the first 32-posting slice of up to 8 lists is
-      //      fetched up front so that one memory latency covers all of them ----------------------
-      for (uint32_t i0 = 0; i0 < nt; i0 += 8) {
-        uint32_t pd[8];
-        float pw[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t i = i0 + u;
-          pd[u] = 0xFFFFFFFFu;
-          pw[u] = 0.0f;
-          if (i < nt && tnxt[i] < bend) {
-            const uint32_t pp = tcur[i] + (uint32_t)wg * 32 + lane;
-            if (pp < tend[i]) {
-              pd[u] = __ldg(p.doc_ids + tbase[i] + pp);
-              pw[u] = __ldg(p.w + tbase[i] + pp);
-            }
-          }
+      // ---- term passes, ascending term id (SPEC §3 order); a pass never writes a document twice -----------
+      for (uint32_t i = 0; i < nt; ++i) {
+        if (tnxt[i] >= bend) continue;  // warp-uniform: the list has nothing in this block
+        const uint32_t slot = tden[i];
+        if (slot != OI_BM25_NONE) {
+          dense_pass(p.dense + (size_t)slot * p.dense_stride + bbase, acc, R, lane);
+          __syncwarp();
+          if (lane == 0) tnxt[i] = bend < p.n_docs ? bend : OI_BM25_NONE;
+        } else {
+          uint32_t pos_new, nxt;
+          sparse_pass(p.post, tbase[i], tcur[i], tend[i], bbase, bend, acc, lane, &pos_new, &nxt);
+          __syncwarp();
+          if (lane == 0) { tcur[i] = pos_new; tnxt[i] = nxt; }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t i = i0 + u;
-          if (i >= nt || tnxt[i] >= bend) continue;  // group-uniform: this list has nothing in the block
-          uint32_t n, fo;
-          const bool full0 = __shfl_sync(0xFFFFFFFFu, pd[u], 31) < bend;
-          if (!full0) {
-            const bool in = pd[u] < bend;
-            if (in) {
-              float *a = acc + (pd[u] - bbase);
-              *a = *a + pw[u];
-            }
-            n = __popc(__ballot_sync(0xFFFFFFFFu, in));  // <= 31
-            fo = __shfl_sync(0xFFFFFFFFu, pd[u], n);
-          } else {
-            float *a = acc + (pd[u] - bbase);
-            *a = *a + pw[u];
-            const u64 base = tbase[i];
-            n = 32 + walk_term(p.doc_ids + base, p.w + base, tcur[i] + (uint32_t)n_warps * 32, tend[i], bbase, bend,
-                               acc, wg, n_warps, lane, &fo);
-          }
-          g.sync();  // every read of tcur[i] / tnxt[i] and every add of this pass is done
-          if (lane == 0) {
-            if (n) atomicAdd(&tcur[i], n);
-            atomicMin(&tnew[i], fo);
-          }
-        }
-      }
-      g.sync();
-      for (uint32_t i = g.tid; i < nt; i += GS) {
-        if (tnxt[i] < bend) { tnxt[i] = tnew[i]; tnew[i] = 0xFFFFFFFFu; }
+        __syncwarp();
       }
       // ---- selection: positive scores that beat the running threshold -------------------------
       const u64 thr = max(ctl->thr, ld_relaxed_u64(p.gthr + q));
       const float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
       const uint32_t cnt0 = ctl->cnt;
       const float4 *acc4 = reinterpret_cast<const float4 *>(acc);
-      g.sync();
+      __syncwarp();
       // optimistic pass: push with a bounds check; in steady state only a handful survive
-      for (uint32_t j = g.tid; j < R / 4; j += GS) {
+      for (uint32_t j = lane; j < R / 4; j += 32) {
         const float4 v = acc4[j];
         const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
         if (m4 > 0.0f && m4 >= tsc) {
@@ -355,20 +335,20 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
           }
         }
       }
-      g.sync();
+      __syncwarp();
       if (ctl->cnt > cap) {
         // overflow (cold threshold): drop this block's pushes and redo it in spans that cannot
         // overflow the buffer, compacting between spans
-        g.sync();
-        if (g.tid == 0) ctl->cnt = cnt0;
-        g.sync();
+        __syncwarp();
+        if (lane == 0) ctl->cnt = cnt0;
+        __syncwarp();
         const uint32_t span_all = bend - bbase;
         uint32_t b0 = 0;
         while (b0 < span_all) {
           const uint32_t span = min(span_all - b0, cap - ctl->cnt);
           const u64 t2 = max(thr, ctl->thr);
-          g.sync();
-          for (uint32_t j = b0 + g.tid; j < b0 + span; j += GS) {
+          __syncwarp();
+          for (uint32_t j = b0 + lane; j < b0 + span; j += 32) {
             const float sc = acc[j];
             if (sc > 0.0f) {
               const u64 key = oi_make_key(sc, p.doc_base + bbase + j);
@@ -376,26 +356,26 @@ __global__ void __launch_bounds__(OI_BM25_THREADS, 1) bm25_blocked_kernel(const 
             }
           }
           b0 += span;
-          g.sync();
+          __syncwarp();
           if (ctl->cnt > cap / 2) {
             grp_compact(cand, ctl, cap, k, g);
-            if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
+            if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
           }
         }
       } else if (ctl->cnt > cap / 2) {
         grp_compact(cand, ctl, cap, k, g);
-        if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
+        if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
       }
       float4 *accw = reinterpret_cast<float4 *>(acc);
-      for (uint32_t j = g.tid; j < R / 4; j += GS) accw[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      g.sync();
+      for (uint32_t j = lane; j < R / 4; j += 32) accw[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      __syncwarp();
     }
     // ---- item done: publish the sorted list ---------------------------------------------------
     grp_compact(cand, ctl, cap, k, g);
-    if (g.tid == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
+    if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
     u64 *out = p.lists + ((size_t)s * p.nq + q) * k;
     const uint32_t cnt = ctl->cnt;
-    for (uint32_t i = g.tid; i < k; i += GS) out[i] = i < cnt ? cand[i] : 0ull;
+    for (uint32_t i = lane; i < k; i += 32) out[i] = i < cnt ? cand[i] : 0ull;
   }
 }
 
@@ -429,7 +409,8 @@ __global__ void bm25_prep_queries_kernel(const uint32_t *q_terms, const uint32_t
 // per-posting folded weight, SPEC §3 association, one IEEE op per line (file built with -fmad=false)
 __global__ void bm25_weights_kernel(const u64 *term_off, const uint32_t *doc_ids, const uint32_t *tfs,
                                     const uint32_t *doc_len, const float *idf, uint32_t n_terms, u64 n_postings,
-                                    float k1, float b, float avgdl, float *w) {
+                                    float k1, float b, float avgdl, float *w, uint2 *post, const int *dense_slot, float *dense,
+                                    uint32_t dense_stride) {
   const float one_minus_b = 1.0f - b;
   const float k1p1 = k1 + 1.0f;
   for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < n_postings; p += (u64)gridDim.x * blockDim.x) {
@@ -448,7 +429,11 @@ __global__ void bm25_weights_kernel(const u64 *term_off, const uint32_t *doc_ids
     const float num = tf * k1p1;
     const float den = tf + norm;
     const float qv = num / den;
-    w[p] = idf[lo] * qv;
+    const float wv = idf[lo] * qv;
+    w[p] = wv;
+    post[p] = make_uint2(doc_ids[p], __float_as_uint(wv));
+    const int slot = dense_slot[lo];
+    if (slot >= 0) dense[(size_t)slot * dense_stride + doc_ids[p]] = wv;
   }
 }
 
@@ -557,6 +542,7 @@ void oi_bm25_free(oi_index *h) {
   OiBm25 *b = h->bm25;
   if (!b) return;
   cudaFree(b->d_term_off); cudaFree(b->d_doc_ids); cudaFree(b->d_tfs); cudaFree(b->d_doc_len); cudaFree(b->d_w);
+  cudaFree(b->d_post); cudaFree(b->d_dense); cudaFree(b->d_dense_slot);
   cudaFree(b->d_qterms); cudaFree(b->d_qnt); cudaFree(b->d_gthr); cudaFree(b->d_counter); cudaFree(b->d_lists);
   cudaFree(b->d_in_terms); cudaFree(b->d_in_offs);
   delete b;
@@ -777,12 +763,39 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
     const double d = (double)df[t];
     idf[t] = df[t] == 0 ? 0.0f : (float)std::log(1.0 + ((double)N - d + 0.5) / (d + 0.5));
   }
+  // dense columns: the terms present in at least a quarter of this shard's documents (at most 16, densest first)
+  std::vector<int> slot(b->n_terms, -1);
+  {
+    std::vector<u64> off((size_t)b->n_terms + 1);
+    BM_CK(cudaMemcpyAsync(off.data(), b->d_term_off, off.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    BM_CK(cudaStreamSynchronize(st));
+    std::vector<std::pair<u64, uint32_t>> heavy;
+    const u64 min_df = std::max<u64>((u64)h->desc.n_docs / 4, 1024);
+    for (uint32_t t = 0; t < b->n_terms; ++t)
+      if (off[t + 1] - off[t] >= min_df) heavy.push_back({off[t + 1] - off[t], t});
+    std::sort(heavy.begin(), heavy.end(), [](const std::pair<u64, uint32_t> &x, const std::pair<u64, uint32_t> &y) { return x.first > y.first; });
+    if (heavy.size() > OI_BM25_MAX_DENSE) heavy.resize(OI_BM25_MAX_DENSE);
+    if (h->bm25_variant == 100) heavy.clear();  // tuning / tests: no dense columns
+    for (size_t i = 0; i < heavy.size(); ++i) slot[heavy[i].second] = (int)i;
+    b->n_dense = (uint32_t)heavy.size();
+  }
+  b->dense_stride = (uint32_t)(((size_t)h->desc.n_docs + OI_BM25_ACC_FLOATS - 1) / OI_BM25_ACC_FLOATS * OI_BM25_ACC_FLOATS);
+  cudaFree(b->d_post); cudaFree(b->d_dense); cudaFree(b->d_dense_slot);
+  b->d_post = nullptr; b->d_dense = nullptr; b->d_dense_slot = nullptr;
+  const size_t dense_elems = (size_t)std::max<uint32_t>(b->n_dense, 1) * b->dense_stride;
+  BM_CK(cudaMalloc(&b->d_post, ((size_t)b->n_postings + 2) * sizeof(uint2)));
+  BM_CK(cudaMalloc(&b->d_dense, std::max<size_t>(dense_elems, 4) * sizeof(float)));
+  BM_CK(cudaMalloc(&b->d_dense_slot, (size_t)b->n_terms * sizeof(int)));
+  BM_CK(cudaMemsetAsync(b->d_post, 0xFF, ((size_t)b->n_postings + 2) * sizeof(uint2), st));
+  BM_CK(cudaMemsetAsync(b->d_dense, 0, std::max<size_t>(dense_elems, 4) * sizeof(float), st));
+  BM_CK(cudaMemcpyAsync(b->d_dense_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   float *d_idf = nullptr;
   BM_CK(cudaMalloc(&d_idf, (size_t)b->n_terms * sizeof(float)));
   cudaError_t e = cudaMemcpyAsync(d_idf, idf.data(), idf.size() * sizeof(float), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && b->n_postings) {
     bm25_weights_kernel<<<grid_for(b->n_postings, 256, h->num_sms), 256, 0, st>>>(b->d_term_off, b->d_doc_ids, b->d_tfs, b->d_doc_len, d_idf,
-                                                                                  b->n_terms, b->n_postings, params->k1, params->b, avgdl, b->d_w);
+                                                                                  b->n_terms, b->n_postings, params->k1, params->b, avgdl, b->d_w,
+                                                                                  b->d_post, b->d_dense_slot, b->d_dense, b->dense_stride);
     ++h->launches;
     e = cudaGetLastError();
   }
@@ -829,22 +842,22 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   BM_CK(cudaGetLastError());
 
   Bm25Params p;
-  p.term_off = b->d_term_off; p.doc_ids = b->d_doc_ids; p.w = b->d_w;
+  p.term_off = b->d_term_off; p.doc_ids = b->d_doc_ids; p.post = b->d_post;
+  p.dense = b->d_dense; p.dense_slot = b->d_dense_slot; p.dense_stride = b->dense_stride;
   p.qterms = b->d_qterms; p.qnt = b->d_qnt; p.gthr = b->d_gthr; p.counter = b->d_counter; p.lists = b->d_lists;
   p.n_docs = (uint32_t)h->desc.n_docs; p.doc_base = (uint32_t)h->desc.doc_base; p.nq = nq; p.k = k;
   uint32_t cap = 256;
   while (cap < 2 * k) cap <<= 1;
   p.cap = cap;
-  // groups per CTA: as many as there are queries to spread (up to 16), bounded by 64 KB of candidates
-  uint32_t ng = 1;
-  while (ng < 16 && ng < nq) ng <<= 1;
+  // one warp per work item; as many warps per CTA as 64 KB of candidate buffers allow (16 for k <= 256)
+  uint32_t ng = 16;
   while (ng > 1 && ng * cap > 8192) ng >>= 1;
-  if (h->bm25_variant >= 1 && h->bm25_variant <= 16) {  // tuning override: groups per CTA
+  if (h->bm25_variant >= 1 && h->bm25_variant <= 16) {  // tuning override: warps per CTA
     uint32_t f = 1;
     while (f * 2 <= (uint32_t)h->bm25_variant) f <<= 1;
     if (f * cap <= 8192) ng = f;
   }
-  p.group_size = OI_BM25_THREADS / ng;
+  p.ng = ng;
   p.R = OI_BM25_ACC_FLOATS / ng;
   p.n_blocks = (p.n_docs + p.R - 1) / p.R;
   if (p.n_blocks == 0) p.n_blocks = 1;
@@ -861,7 +874,7 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   uint32_t grid = (uint32_t)h->num_sms;
   const uint32_t ctas_useful = (p.S * nq + ng - 1) / ng;
   if (grid > ctas_useful) grid = ctas_useful;
-  bm25_blocked_kernel<<<grid, OI_BM25_THREADS, smem, st>>>(p);
+  bm25_blocked_kernel<<<grid, ng * 32, smem, st>>>(p);
   ++h->launches;
   BM_CK(cudaGetLastError());
   BM_CK(oi_launch_merge_shards(b->d_lists, p.S, nq, k, d_out_keys, st, &h->launches));

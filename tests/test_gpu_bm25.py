@@ -68,6 +68,22 @@ def test_bm25_parity_bit_exact(oi, n, vocab, k, nq, groups):
             assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
 
 
+@pytest.mark.parametrize("n,vocab,k,nq", [(30000, 800, 100, 20), (70000, 20000, 10, 5), (9000, 2000, 1000, 2)])
+def test_bm25_sparse_only_path_bit_exact(oi, n, vocab, k, nq):
+    """bm25_variant = 100 builds no dense weight columns: every term, however common, walks its postings"""
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = _weights(corp, n)
+    qs = O.synth_query_terms(nq, 8, corp["cdf"])
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=nq) as ix:
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.set_option("bm25_variant", 100)
+        ix.bm25_finalize()
+        ids, sc = ix.search_bm25(qs, k)
+    wi, ws = _oracle_lists(corp, w, qs, n, k)
+    assert np.array_equal(ids, wi)
+    assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
+
+
 def test_bm25_edge_cases(oi):
     n, vocab, k = 12000, 1500, 20
     corp = O.synth_bm25_corpus(n, vocab)
