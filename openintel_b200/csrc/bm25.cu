@@ -139,7 +139,8 @@ struct Bm25Params {
   u64 *lists;                 // [S][nq][k]
   uint32_t n_docs, doc_base, nq, k;
   uint32_t cap;               // candidate buffer keys per warp (power of two, >= 2k)
-  uint32_t R;                 // docs per block
+  uint32_t R;                 // docs per block (a power of two)
+  uint32_t r_shift;           // log2(R)
   uint32_t J;                 // blocks per super-range
   uint32_t S;                 // super-ranges
   uint32_t n_blocks;
@@ -156,17 +157,20 @@ __device__ __forceinline__ uint4 ldg_post2(const uint2 *p) {
 // the block.  *pos_out = the new cursor, *nxt_out = the document there (NONE at the end of the list).
 __device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 base, uint32_t pos, uint32_t end, uint32_t bbase,
                                             uint32_t bend, float *acc, int lane, uint32_t *pos_out, uint32_t *nxt_out) {
-  const u64 g0 = base + pos, gend = base + end;
-  u64 a = g0 & ~1ull;
-  uint32_t skip = (uint32_t)(g0 - a);  // a leading slot below the cursor (0 or 1)
+  // list-local 32-bit slot numbers over a 16-byte-aligned view of the list: slot j = posting (j - par)
+  const uint32_t par = (uint32_t)(base & 1ull);
+  const uint2 *lp = post + (base - par);
+  const uint32_t j0 = pos + par, jend = end + par;  // [j0, jend) = the postings still to consume
+  uint32_t a = j0 & ~1u;
+  uint32_t skip = j0 - a;  // a leading slot below the cursor (0 or 1)
   uint32_t applied = 0, nxt = OI_BM25_NONE;
   for (;;) {
-    const u64 idx = a + 2u * (uint32_t)lane;
+    const uint32_t idx = a + 2u * (uint32_t)lane;
     uint4 v = make_uint4(OI_BM25_NONE, 0u, OI_BM25_NONE, 0u);
-    if (idx < gend) v = ldg_post2(post + idx);   // the array is padded, so reading the pair is always in bounds
-    if (idx + 1 >= gend) v.z = OI_BM25_NONE;      // second slot belongs to the next list
-    if (idx < g0) v.x = OI_BM25_NONE;             // leading slot below the cursor: skipped, not applied
-    const bool in0 = idx >= g0 && v.x < bend, in1 = v.z < bend;
+    if (idx < jend) v = ldg_post2(lp + idx);     // the array is padded, so reading the pair is always in bounds
+    if (idx + 1 >= jend) v.z = OI_BM25_NONE;      // second slot belongs to the next list
+    if (idx < j0) v.x = OI_BM25_NONE;             // leading slot below the cursor: skipped, not applied
+    const bool in0 = v.x < bend, in1 = v.z < bend;
     if (in0) {
       float *x = acc + (v.x - bbase);
       *x = *x + __uint_as_float(v.y);  // SPEC §3: one f32 add, previous terms first
@@ -181,7 +185,7 @@ __device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 
       const uint32_t sl = skip + n;
       const uint32_t d = (sl & 1u) ? v.z : v.x;
       nxt = __shfl_sync(0xFFFFFFFFu, d, (int)(sl >> 1));
-      if (a + sl >= gend) nxt = OI_BM25_NONE;
+      if (a + sl >= jend) nxt = OI_BM25_NONE;
       break;
     }
     a += 64;
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(512, 1) bm25_blocked_kernel(const Bm25Params p
       for (uint32_t i = lane; i < nt; i += 32) mn = min(mn, tnxt[i]);
       mn = __reduce_min_sync(0xFFFFFFFFu, mn);
       if (mn == OI_BM25_NONE) break;
-      blk = max(blk, mn / R);
+      blk = max(blk, mn >> p.r_shift);
       if (blk >= blk1) break;
       const uint32_t bbase = blk * R;
       const uint32_t bend = min(p.n_docs, bbase + R);
@@ -317,31 +321,51 @@ __global__ void __launch_bounds__(512, 1) bm25_blocked_kernel(const Bm25Params p
       // ---- selection: positive scores that beat the running threshold -------------------------
       const u64 thr = max(ctl->thr, ld_relaxed_u64(p.gthr + q));
       const float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
-      const uint32_t cnt0 = ctl->cnt;
-      const float4 *acc4 = reinterpret_cast<const float4 *>(acc);
       __syncwarp();
-      // optimistic pass: push with a bounds check; in steady state only a handful survive
-      for (uint32_t j = lane; j < R / 4; j += 32) {
-        const float4 v = acc4[j];
-        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-        if (m4 > 0.0f && m4 >= tsc) {
-          const float sc4[4] = {v.x, v.y, v.z, v.w};
+      // one pass reads, tests and clears the block, 4 x 128 bits per lane per step.  In steady state only a
+      // handful of scores survive the threshold; a survivor that finds the buffer full is written back, so
+      // the (rare) overflow path below sees exactly the scores that still have to be ranked.
+      float4 *accw = reinterpret_cast<float4 *>(acc);
+      const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      for (uint32_t jb = 0; jb < R / 4; jb += 128) {
+        float4 vv[4];
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            if (sc4[c4] > 0.0f && sc4[c4] >= tsc) {
-              const u64 key = oi_make_key(sc4[c4], p.doc_base + bbase + 4 * j + c4);
-              if (key > thr) { const uint32_t at = atomicAdd(&ctl->cnt, 1u); if (at < cap) cand[at] = key; }
+        for (int u = 0; u < 4; ++u) vv[u] = accw[jb + 32 * u + lane];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) accw[jb + 32 * u + lane] = zero4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 v = vv[u];
+          const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+          if (m4 > 0.0f && m4 >= tsc) {
+            const uint32_t j = jb + 32 * u + lane;
+            const float sc4[4] = {v.x, v.y, v.z, v.w};
+            float back[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            bool any_back = false;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              if (sc4[c4] > 0.0f && sc4[c4] >= tsc) {
+                const u64 key = oi_make_key(sc4[c4], p.doc_base + bbase + 4 * j + c4);
+                if (key > thr) {
+                  const uint32_t at = atomicAdd(&ctl->cnt, 1u);
+                  if (at < cap) cand[at] = key;
+                  else { back[c4] = sc4[c4]; any_back = true; }
+                }
+              }
             }
+            if (any_back) accw[j] = make_float4(back[0], back[1], back[2], back[3]);
           }
         }
       }
       __syncwarp();
       if (ctl->cnt > cap) {
-        // overflow (cold threshold): drop this block's pushes and redo it in spans that cannot
-        // overflow the buffer, compacting between spans
+        // overflow (cold threshold): the buffer holds `cap` valid keys and the scores that did not fit are
+        // back in acc[]; rank those in spans that cannot overflow the buffer, compacting between spans
         __syncwarp();
-        if (lane == 0) ctl->cnt = cnt0;
+        if (lane == 0) ctl->cnt = cap;
         __syncwarp();
+        grp_compact(cand, ctl, cap, k, g);
+        if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
         const uint32_t span_all = bend - bbase;
         uint32_t b0 = 0;
         while (b0 < span_all) {
@@ -362,12 +386,11 @@ __global__ void __launch_bounds__(512, 1) bm25_blocked_kernel(const Bm25Params p
             if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
           }
         }
+        for (uint32_t j = lane; j < R / 4; j += 32) accw[j] = zero4;  // the written-back scores are ranked now
       } else if (ctl->cnt > cap / 2) {
         grp_compact(cand, ctl, cap, k, g);
         if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
       }
-      float4 *accw = reinterpret_cast<float4 *>(acc);
-      for (uint32_t j = lane; j < R / 4; j += 32) accw[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       __syncwarp();
     }
     // ---- item done: publish the sorted list ---------------------------------------------------
@@ -859,6 +882,8 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   }
   p.ng = ng;
   p.R = OI_BM25_ACC_FLOATS / ng;
+  p.r_shift = 0;
+  while ((1u << p.r_shift) < p.R) ++p.r_shift;
   p.n_blocks = (p.n_docs + p.R - 1) / p.R;
   if (p.n_blocks == 0) p.n_blocks = 1;
   const uint32_t groups = (uint32_t)h->num_sms * ng;
