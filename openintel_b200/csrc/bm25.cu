@@ -889,6 +889,7 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   const uint32_t groups = (uint32_t)h->num_sms * ng;
   uint32_t S = (3 * groups + nq - 1) / nq;
   if (S < 1) S = 1;
+  if (S > 512) S = 512;  // the per-query merge handles up to 512 sorted lists on its fast path
   if (S > p.n_blocks) S = p.n_blocks;
   p.J = (p.n_blocks + S - 1) / S;
   p.S = (p.n_blocks + p.J - 1) / p.J;

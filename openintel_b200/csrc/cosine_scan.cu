@@ -87,6 +87,83 @@ struct SelState {
   uint32_t is_last;
 };
 
+// Exact top-k of G sorted (descending, 0-padded) lists of k keys, list c at lists + c * stride.  On return
+// S.buf[0 .. S.cnt) holds the result, sorted.  Called by the `nthreads` threads of barrier `bar`.
+//  (1) sampling bound: if m lists each hold >= ceil(k/m) keys >= T then at least k keys are >= T;
+//  (2) every list is sorted, so its keys above the bound are a prefix: measure the prefixes (gallop + bisect,
+//      ~3 dependent loads per list) and, when they fit the buffer together — the common case, a few hundred
+//      keys — copy them in place; otherwise (heavy ties, skewed lists, G > OI_SEL_CAP) stream every key
+//      through the filter + buffer.  One CTA does this per query, so it has to take microseconds.
+__device__ void merge_sorted_lists(SelState &S, const u64 *lists, uint32_t G, size_t stride, uint32_t k, int tid, int nthreads, int bar) {
+  bool fits = false;
+  if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
+  oi_bar_sync(bar, nthreads);
+  if (G <= OI_SEL_CAP / 4) {
+    const uint32_t m = max(1u, G / 2);
+    const uint32_t j = (k + m - 1) / m - 1;
+    const uint32_t gp = oi_next_pow2(G);
+    for (uint32_t c = tid; c < gp; c += nthreads) S.buf[c] = c < G ? __ldcg(lists + (size_t)c * stride + j) : 0ull;
+    oi_bar_sync(bar, nthreads);
+    oi_bitonic_desc(S.buf, gp, tid, nthreads, bar);
+    const u64 T = S.buf[m - 1];
+    oi_bar_sync(bar, nthreads);
+    const u64 bound = T > 0 ? T - 1 : 0;
+    uint32_t *s_n = reinterpret_cast<uint32_t *>(S.buf + OI_SEL_CAP / 2);  // [G] prefix lengths, then [G] offsets
+    uint32_t *s_off = s_n + G;
+    for (uint32_t c = tid; c < G; c += nthreads) {
+      const u64 *list = lists + (size_t)c * stride;
+      uint32_t lo = 0, hi = 1;  // keys [0, lo) pass; find the first position that does not
+      while (hi <= k && __ldcg(list + hi - 1) > bound) { lo = hi; hi <<= 1; }
+      hi = min(hi - 1, k);      // position hi (if < k) fails or is the end
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldcg(list + mid) > bound) lo = mid + 1; else hi = mid;
+      }
+      s_n[c] = lo;
+    }
+    oi_bar_sync(bar, nthreads);
+    if (tid == 0) {
+      uint32_t sum = 0;
+      for (uint32_t c = 0; c < G; ++c) { s_off[c] = sum; sum += s_n[c]; }
+      S.is_last = sum;  // broadcast slot for the total
+    }
+    oi_bar_sync(bar, nthreads);
+    const uint32_t total_pass = S.is_last;
+    fits = total_pass <= OI_SEL_CAP / 2;
+    if (fits) {
+      for (uint32_t c = tid; c < G; c += nthreads) {
+        const u64 *list = lists + (size_t)c * stride;
+        const uint32_t n = s_n[c], o = s_off[c];
+        for (uint32_t i = 0; i < n; ++i) S.buf[o + i] = __ldcg(list + i);
+      }
+      oi_bar_sync(bar, nthreads);
+      if (tid == 0) S.cnt = total_pass;
+      oi_bar_sync(bar, nthreads);
+      oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
+    } else {
+      if (tid == 0) S.thr = bound;
+      oi_bar_sync(bar, nthreads);
+    }
+  }
+  if (!fits) {
+    const u64 total = (u64)G * k;
+    u64 base = 0;
+    while (base < total) {
+      // snapshot (cnt, thr) before anybody pushes: loop bounds must be CTA-uniform
+      const uint32_t span = (uint32_t)min(total - base, (u64)((uint32_t)OI_SEL_CAP - S.cnt));
+      const u64 thr = S.thr;
+      oi_bar_sync(bar, nthreads);
+      for (u64 i = base + tid; i < base + span; i += nthreads) {
+        const u64 key = __ldcg(lists + (i / k) * stride + (i % k));
+        if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
+      }
+      base += span;
+      oi_bar_sync(bar, nthreads);
+      if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
+    }
+  }
+}
+
 // Ends a scan CTA: final compaction, publish the sorted local list, and — in the last CTA to
 // arrive — merge all lists into out_keys.  Called by the `nthreads` threads of barrier `bar`.
 __device__ void scan_epilogue(SelState &S, const OiScanParams &p, int tid, int nthreads, int bar) {
@@ -104,74 +181,8 @@ __device__ void scan_epilogue(SelState &S, const OiScanParams &p, int tid, int n
   oi_bar_sync(bar, nthreads);
   if (!S.is_last) return;
   __threadfence();
-
-  // ---- last CTA: exact top-k of G sorted lists ---------------------------------------------
-  const uint32_t G = gridDim.x;
-  // (1) sampling bound: if m lists each hold >= ceil(k/m) keys >= T then >= k keys are >= T.
-  const uint32_t m = max(1u, G / 2);
-  const uint32_t j = (k + m - 1) / m - 1;
-  const uint32_t gp = oi_next_pow2(G);
-  for (uint32_t c = tid; c < gp; c += nthreads) S.buf[c] = c < G ? __ldcg(p.cand + (size_t)c * k + j) : 0ull;
-  oi_bar_sync(bar, nthreads);
-  oi_bitonic_desc(S.buf, gp, tid, nthreads, bar);
-  const u64 T = S.buf[m - 1];
-  oi_bar_sync(bar, nthreads);
-  if (tid == 0) { S.cnt = 0; S.thr = T > 0 ? T - 1 : 0; }
-  oi_bar_sync(bar, nthreads);
-  // (2) every list is sorted, so its keys above the bound are a prefix.  Measure the prefixes (gallop +
-  //     bisect: ~3 dependent loads per list), and when they fit the buffer together copy them in place —
-  //     the common case, a few hundred keys.  One CTA does this for every query, so it must take
-  //     microseconds: it is the serial stage of the whole scan pipeline.
-  const u64 bound = S.thr;
-  uint32_t *s_n = reinterpret_cast<uint32_t *>(S.buf + OI_SEL_CAP / 2);  // [G] prefix lengths, then [G] offsets
-  uint32_t *s_off = s_n + G;
-  for (uint32_t c = tid; c < G; c += nthreads) {
-    const u64 *list = p.cand + (size_t)c * k;
-    uint32_t lo = 0, hi = 1;  // keys [0, lo) pass; find the first position that does not
-    while (hi <= k && __ldcg(list + hi - 1) > bound) { lo = hi; hi <<= 1; }
-    hi = min(hi - 1, k);      // position hi (if < k) fails or is the end
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldcg(list + mid) > bound) lo = mid + 1; else hi = mid;
-    }
-    s_n[c] = lo;
-  }
-  oi_bar_sync(bar, nthreads);
-  if (tid == 0) {
-    uint32_t sum = 0;
-    for (uint32_t c = 0; c < G; ++c) { s_off[c] = sum; sum += s_n[c]; }
-    S.is_last = sum;  // reused as the broadcast slot for the total
-  }
-  oi_bar_sync(bar, nthreads);
-  const uint32_t total_pass = S.is_last;
-  if (total_pass <= OI_SEL_CAP / 2) {
-    for (uint32_t c = tid; c < G; c += nthreads) {
-      const u64 *list = p.cand + (size_t)c * k;
-      const uint32_t n = s_n[c], o = s_off[c];
-      for (uint32_t i = 0; i < n; ++i) S.buf[o + i] = __ldcg(list + i);
-    }
-    oi_bar_sync(bar, nthreads);
-    if (tid == 0) S.cnt = total_pass;
-    oi_bar_sync(bar, nthreads);
-    oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
-  } else {
-    // many keys above the bound (heavy ties / skewed lists): stream everything through the filter + buffer
-    const uint32_t total = G * k;
-    uint32_t base = 0;
-    while (base < total) {
-      // snapshot (cnt, thr) before anybody pushes: loop bounds must be CTA-uniform
-      const uint32_t span = min(total - base, (uint32_t)OI_SEL_CAP - S.cnt);
-      const u64 thr = S.thr;
-      oi_bar_sync(bar, nthreads);
-      for (uint32_t i = base + tid; i < base + span; i += nthreads) {
-        u64 key = __ldcg(p.cand + i);
-        if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
-      }
-      base += span;
-      oi_bar_sync(bar, nthreads);
-      if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, nthreads, bar);
-    }
-  }
+  // ---- last CTA: exact top-k of the gridDim.x sorted lists -------------------------------------
+  merge_sorted_lists(S, p.cand, gridDim.x, k, k, tid, nthreads, bar);
   // (3) emit and re-arm the per-query control words for the next launch
   for (uint32_t i = tid; i < k; i += nthreads) p.out_keys[i] = i < S.cnt ? S.buf[i] : 0ull;
   if (tid == 0) { *p.ticket = 0; *p.tile_ctr = 0; *p.gthr = 0ull; }
@@ -568,28 +579,13 @@ __global__ void unpack_keys_kernel(const u64 *keys, uint32_t n, uint32_t *ids, f
   scores[i] = key ? oi_key_score(key) : 0.0f;
 }
 
-// One CTA per query: exact top-k of world sorted lists (world * k <= a few thousand keys).
+// One CTA per query: exact top-k of `world` sorted lists (shards after the all-gather, or the per-item lists
+// of the BM25 kernel), list r of query qi at gathered + (r * nq + qi) * k.
 __global__ void __launch_bounds__(256) merge_shards_kernel(const u64 *gathered, uint32_t world, uint32_t nq, uint32_t k, u64 *out) {
   __shared__ SelState S;
   const int tid = threadIdx.x;
   const uint32_t qi = blockIdx.x;
-  if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
-  __syncthreads();
-  const uint32_t total = world * k;
-  uint32_t base = 0;
-  while (base < total) {
-    const uint32_t span = min(total - base, (uint32_t)OI_SEL_CAP - S.cnt);
-    const u64 thr = S.thr;
-    __syncthreads();
-    for (uint32_t i = base + tid; i < base + span; i += 256) {
-      const uint32_t r = i / k, j = i % k;
-      u64 key = gathered[((size_t)r * nq + qi) * k + j];
-      if (key > thr) oi_sel_push(S.buf, &S.cnt, key);
-    }
-    base += span;
-    __syncthreads();
-    if (S.cnt > OI_SEL_CAP / 2 || base >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
-  }
+  merge_sorted_lists(S, gathered + (size_t)qi * k, world, (size_t)nq * k, k, tid, 256, 0);
   for (uint32_t i = tid; i < k; i += 256) out[(size_t)qi * k + i] = i < S.cnt ? S.buf[i] : 0ull;
 }
 
