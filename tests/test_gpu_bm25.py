@@ -202,3 +202,56 @@ def test_rrf_short_and_disjoint_lists(oi):
         assert np.array_equal(ids[j], e_ids) and np.array_equal(rrf[j].view(np.uint32), e_val.view(np.uint32))
         assert np.array_equal(rc[j], e_rc) and np.array_equal(rb[j], e_rb)
     assert np.all(rb[1] == 0)
+
+
+def test_full_size_config3_properties(oi):
+    """BASELINE config 3 scale (10M docs, 1M-term Zipf vocabulary, 8-term queries) through size-independent
+    properties: lists are sorted and duplicate-free, every reported score equals the oracle's f32 sum of the
+    folded weights read back from the device (bit for bit), and the result equals the merge of the results of
+    two half-corpus shards scored with GLOBAL statistics (checksum of checksums)."""
+    n, vocab, k, nq = 10_000_000, 1_000_000, 100, 32
+    cdf = O.zipf_cdf(vocab)
+    qs = np.concatenate([O.synth_query_terms(nq // 2, 8, cdf), O.synth_query_terms(nq // 2, 8, cdf, uniform=True)])
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=nq) as ix:
+        ix.synth_bm25(O.SEED, vocab, cdf)
+        df, sdl, npost = ix.bm25_local_stats()
+        ix.bm25_finalize()
+        ids, sc = ix.search_bm25(qs, k)
+        got = ix.read_bm25(npost)
+    avgdl = np.float32(np.float64(sdl) / n)
+    for j in range(nq):
+        valid = ids[j] != oi.NO_DOC
+        assert np.all(np.diff(sc[j][valid]) <= 0) and len(set(ids[j][valid])) == int(valid.sum())
+        # ties broken by ascending doc id
+        same = np.diff(sc[j][valid]) == 0
+        assert np.all(np.diff(ids[j][valid].astype(np.int64))[same] > 0)
+    # recompute a sample of reported scores from the device's own CSR + weights in SPEC order (ascending term id)
+    to, di, w = got["term_offsets"], got["doc_ids"], got["weights"]
+    for j in (0, 5, nq // 2, nq - 1):
+        terms = sorted(set(int(t) for t in qs[j]))
+        for i in (0, 1, k // 2, k - 1):
+            d = ids[j][i]
+            if d == oi.NO_DOC:
+                continue
+            s = np.float32(0.0)
+            for t in terms:
+                lo, hi = int(to[t]), int(to[t + 1])
+                p = lo + int(np.searchsorted(di[lo:hi], d))
+                if p < hi and di[p] == d:
+                    s = np.float32(s + w[p])
+            assert s.view(np.uint32) == sc[j][i].view(np.uint32), (j, i, d)
+    # two half shards with global statistics reproduce the unsharded lists exactly
+    halves = []
+    for base in (0, n // 2):
+        with oi.GpuIndex(n_docs=n // 2, dim=64, max_k=k, max_batch=nq, doc_base=base) as ix:
+            ix.synth_bm25(O.SEED, vocab, cdf)
+            ix.bm25_finalize(avgdl=float(avgdl), n_docs_global=n, global_df=df)
+            halves.append(ix.search_bm25(qs, k))
+    for j in range(nq):
+        cat_ids = np.concatenate([halves[0][0][j], halves[1][0][j]])
+        cat_sc = np.concatenate([halves[0][1][j], halves[1][1][j]])
+        keep = cat_ids != oi.NO_DOC
+        order = sorted(np.nonzero(keep)[0], key=lambda i: (-float(cat_sc[i]), int(cat_ids[i])))[:k]
+        m = len(order)
+        assert np.array_equal(cat_ids[order], ids[j][:m]) and np.array_equal(cat_sc[order].view(np.uint32), sc[j][:m].view(np.uint32))
+        assert np.all(ids[j][m:] == oi.NO_DOC)

@@ -98,3 +98,35 @@ def test_gemm_edge_cases(oi):
         ids, sc = ix.search_cosine(np.repeat(O.bf16_to_f32(rows[:1]), 4, axis=0), 100)
         for j in range(4):
             assert list(ids[j]) == list(range(10, 110))
+
+
+def test_full_size_config4_properties(oi):
+    """BASELINE config 4 (10M x 768 bf16, batch 256, top-100) through size-independent properties: planted
+    targets come back at rank 1, lists are sorted and duplicate-free, the result equals the merge of the
+    results of two half-size shards, and spot-checked scores equal the oracle's on regenerated rows."""
+    n, dim, k, nq = 10_000_000, 768, 100, 256
+    pq, tgt = O.synth_planted_queries(8, dim, n)
+    q = np.concatenate([pq, O.synth_rows_f32(nq - 8, dim, stream=1)])
+    with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=nq) as ix:
+        ix.synth_embeddings(O.SEED)
+        ids, sc = ix.search_cosine(q, k)
+    for j in range(8):
+        assert ids[j][0] == tgt[j] and sc[j][0] > 0.85
+    for j in range(nq):
+        assert np.all(np.diff(sc[j]) <= 0) and len(set(ids[j])) == k and ids[j].max() < n
+    halves = []
+    for base in (0, n // 2):
+        with oi.GpuIndex(n_docs=n // 2, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=nq, doc_base=base) as ix:
+            ix.synth_embeddings(O.SEED)
+            halves.append(ix.search_cosine(q, k))
+    for j in range(nq):
+        cat_ids = np.concatenate([halves[0][0][j], halves[1][0][j]])
+        cat_sc = np.concatenate([halves[0][1][j], halves[1][1][j]])
+        order = sorted(range(2 * k), key=lambda i: (-cat_sc[i], cat_ids[i]))[:k]
+        assert np.array_equal(cat_ids[order], ids[j]) and np.array_equal(cat_sc[order], sc[j])
+    for j in (0, 9, 100, 255):
+        for i in (0, 1, 50, 99):
+            row = O.synth_rows_bf16(1, dim, first=int(ids[j][i]))
+            want = float(O.cosine_scores_bf16(row, q[j])[0])
+            assert abs(want - sc[j][i]) <= BF16_TOL * max(abs(want), 1e-2)
+            assert abs(want - sc[j][i]) < 2e-5
