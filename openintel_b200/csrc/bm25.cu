@@ -222,7 +222,8 @@ __device__ __forceinline__ void dense_pass(const float *__restrict__ col, float 
 //   u32   tnxt[NG][64]       doc id at the cursor (NONE = exhausted)
 //   u32   tden[NG][64]       dense column of the term (NONE = sparse)
 //   GrpCtl ctl[NG]
-__global__ void __launch_bounds__(512, 1) bm25_blocked_kernel(const Bm25Params p) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params p) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int NG = (int)p.ng;
   const int gi = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(512, 1) bm25_blocked_kernel(const Bm25Params p
   g.bar = 0;
 
   float *acc_all = reinterpret_cast<float *>(s_dyn);
-  u64 *cand_all = reinterpret_cast<u64 *>(s_dyn + sizeof(float) * OI_BM25_ACC_FLOATS);
+  u64 *cand_all = reinterpret_cast<u64 *>(s_dyn + sizeof(float) * (size_t)NG * p.R);
   u64 *tbase_all = cand_all + (size_t)NG * p.cap;
   uint32_t *tcur_all = reinterpret_cast<uint32_t *>(tbase_all + (size_t)NG * OI_BM25_MAX_QTERMS);
   uint32_t *tend_all = tcur_all + NG * OI_BM25_MAX_QTERMS;
@@ -572,7 +573,7 @@ void oi_bm25_free(oi_index *h) {
   h->bm25 = nullptr;
 }
 
-static size_t bm25_lists_cap(const oi_index *h) { return (size_t)3 * h->num_sms * 16 + 64 + 2 * (size_t)h->desc.max_batch; }
+static size_t bm25_lists_cap(const oi_index *h) { return (size_t)3 * h->num_sms * 24 + 64 + 2 * (size_t)h->desc.max_batch; }
 
 static oi_status bm25_alloc_workspace(oi_index *h, OiBm25 *b) {
   const size_t B = h->desc.max_batch;
@@ -872,16 +873,19 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   uint32_t cap = 256;
   while (cap < 2 * k) cap <<= 1;
   p.cap = cap;
-  // one warp per work item; as many warps per CTA as 64 KB of candidate buffers allow (16 for k <= 256)
+  // one warp per work item.  k <= 128: 24 warps per CTA, 1024-document blocks (more warps in flight hide the
+  // L2 latency of the posting loads); larger k: 16 / 8 / 4 warps with 2048 / 4096 / 8192-document blocks,
+  // as many as 64 KB of candidate buffers allow.
   uint32_t ng = 16;
   while (ng > 1 && ng * cap > 8192) ng >>= 1;
-  if (h->bm25_variant >= 1 && h->bm25_variant <= 16) {  // tuning override: warps per CTA
+  p.R = OI_BM25_ACC_FLOATS / ng;
+  if (cap <= 256 && h->bm25_variant != 16) { ng = 24; p.R = 1024; }
+  if (h->bm25_variant >= 1 && h->bm25_variant <= 15) {  // tuning override: warps per CTA (power of two)
     uint32_t f = 1;
     while (f * 2 <= (uint32_t)h->bm25_variant) f <<= 1;
-    if (f * cap <= 8192) ng = f;
+    if (f * cap <= 8192) { ng = f; p.R = OI_BM25_ACC_FLOATS / ng; }
   }
   p.ng = ng;
-  p.R = OI_BM25_ACC_FLOATS / ng;
   p.r_shift = 0;
   while ((1u << p.r_shift) < p.R) ++p.r_shift;
   p.n_blocks = (p.n_docs + p.R - 1) / p.R;
@@ -894,13 +898,15 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   p.J = (p.n_blocks + S - 1) / S;
   p.S = (p.n_blocks + p.J - 1) / p.J;
   if ((size_t)p.S * nq > b->lists_cap) return h->fail(OI_ERR_CUDA, "internal: BM25 list workspace too small (%u x %u)", p.S, nq);
-  const size_t smem = sizeof(float) * OI_BM25_ACC_FLOATS + (size_t)ng * cap * sizeof(u64) +
+  const size_t smem = sizeof(float) * (size_t)ng * p.R + (size_t)ng * cap * sizeof(u64) +
                       (size_t)ng * OI_BM25_MAX_QTERMS * (sizeof(u64) + 4 * sizeof(uint32_t)) + ng * sizeof(GrpCtl);
-  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   uint32_t grid = (uint32_t)h->num_sms;
   const uint32_t ctas_useful = (p.S * nq + ng - 1) / ng;
   if (grid > ctas_useful) grid = ctas_useful;
-  bm25_blocked_kernel<<<grid, ng * 32, smem, st>>>(p);
+  if (ng > 16) bm25_blocked_kernel<768><<<grid, ng * 32, smem, st>>>(p);
+  else bm25_blocked_kernel<512><<<grid, ng * 32, smem, st>>>(p);
   ++h->launches;
   BM_CK(cudaGetLastError());
   BM_CK(oi_launch_merge_shards(b->d_lists, p.S, nq, k, d_out_keys, st, &h->launches));
