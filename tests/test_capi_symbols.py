@@ -33,6 +33,14 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(lib._oi_sig) == syms
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/openintel-gpu-sys is source only (no Rust toolchain here); at least keep its extern block in step
+    with the header"""
+    rs = open(os.path.join(ROOT, "rust", "openintel-gpu-sys", "src", "lib.rs")).read()
+    for s in _declared_symbols():
+        assert ("fn %s(" % s) in rs, "rust -sys crate lacks " + s
+
+
 def test_version_and_no_cpu_fallback(lib):
     assert "sm_100a" in oi.version()
     import torch

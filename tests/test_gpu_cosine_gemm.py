@@ -23,7 +23,8 @@ def _oracle_scores(rows_bf16, q):
     return O.cosine_scores_bf16(rows_bf16, q)
 
 
-@pytest.mark.parametrize("n,dim,nq", [(1000, 128, 5), (4097, 768, 130), (64, 64, 1), (200, 384, 128)])
+@pytest.mark.parametrize("n,dim,nq", [(1000, 128, 5), (4097, 768, 130), (64, 64, 1), (200, 384, 128), (3000, 192, 4), (2500, 512, 9),
+                                      (700, 256, 3)])
 def test_raw_scores_match_oracle(oi, n, dim, nq):
     """every element of the nq x n score matrix (TMEM accumulators dumped by the epilogue)"""
     rows = O.synth_rows_bf16(n, dim)
@@ -130,3 +131,32 @@ def test_full_size_config4_properties(oi):
             want = float(O.cosine_scores_bf16(row, q[j])[0])
             assert abs(want - sc[j][i]) <= BF16_TOL * max(abs(want), 1e-2)
             assert abs(want - sc[j][i]) < 2e-5
+
+
+def test_calls_from_many_threads_on_one_handle(oi):
+    """the reference awaits a port from many tasks on one &self (src/application/analyze.rs:30-37): calls on
+    one handle from several threads are serialised inside the library and each returns its own result"""
+    import threading
+    n, dim, k = 30000, 128, 20
+    rows = O.synth_rows_bf16(n, dim)
+    qs = O.synth_rows_f32(32, dim, stream=1)
+    with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=8) as ix:
+        ix.load_embeddings(rows)
+        want = [ix.search_cosine(qs[8 * t:8 * t + 8], k) for t in range(4)]
+        got = [None] * 4
+        errs = []
+
+        def work(t):
+            try:
+                for _ in range(20):
+                    got[t] = ix.search_cosine(qs[8 * t:8 * t + 8], k)
+                    one = ix.search_cosine(qs[8 * t:8 * t + 1], k)  # the scan path, interleaved with the tensor path
+                    assert np.array_equal(one[0][0], got[t][0][0])
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs
+        for t in range(4):
+            assert np.array_equal(got[t][0], want[t][0]) and np.array_equal(got[t][1], want[t][1])

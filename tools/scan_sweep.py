@@ -41,5 +41,36 @@ def main():
         ix.close()
 
 
+def bf16_single():
+    """single-query scan over a bf16 matrix (the path a bf16 index takes below the tensor-core batch threshold)"""
+    import torch
+    import openintel_b200 as oi
+    dev = torch.device("cuda", 0)
+    n, dim, k, nq = 5_000_000, 768, 100, 3
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(4, nq, dim, generator=g)
+    q = (q / q.norm(dim=2, keepdim=True)).to(dev)
+    ids = torch.empty(nq, k, dtype=torch.int32, device=dev)
+    sc = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ix = oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=nq)
+    ix.synth_embeddings(20261018)
+    for i in range(3):
+        ix.search_cosine_dev(q[i % 4], nq, k, ids, sc, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        ix.search_cosine_dev(q[i % 4], nq, k, ids, sc, st)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 / nq * 1e3
+    print(json.dumps({"workload": "single-query scan, 5M x 768 bf16", "us_per_query": round(us, 1), "GBps": round(n * dim * 2 / us / 1e3, 1)}), flush=True)
+    ix.close()
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "bf16":
+        bf16_single()
+    else:
+        main()
