@@ -172,6 +172,31 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->bm25_variant = (int)value;
     return OI_OK;
   }
+  if (!strcmp(name, "bm25_warps")) {
+    OI_REQUIRE(value >= 0 && value <= 24, "bm25_warps must be in 0..24 (0 = default)");
+    h->bm25_warps = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "bm25_block_docs")) {
+    OI_REQUIRE(value == 0 || (value >= 1024 && value <= 32768 && (value & (value - 1)) == 0), "bm25_block_docs must be 0 or a power of two in 1024..32768");
+    h->bm25_block_docs = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "bm25_dense_div")) {
+    OI_REQUIRE(value >= 0 && value <= 1024, "bm25_dense_div must be in 0..1024 (0 = default)");
+    h->bm25_dense_div = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "bm25_items_per_warp")) {
+    OI_REQUIRE(value >= 0 && value <= 32, "bm25_items_per_warp must be in 0..32 (0 = default)");
+    h->bm25_items_per_warp = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "bm25_stage_slots")) {
+    OI_REQUIRE(value >= -1 && value <= 16, "bm25_stage_slots must be in -1..16 (-1 = default)");
+    h->bm25_stage_slots = (int)value;
+    return OI_OK;
+  }
   return h->fail(OI_ERR_INVALID_ARG, "unknown option '%s'", name);
 }
 

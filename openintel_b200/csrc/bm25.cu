@@ -46,7 +46,7 @@ struct OiBm25 {
   uint32_t *d_tfs = nullptr;      // [P]
   uint32_t *d_doc_len = nullptr;  // [n_docs]
   float *d_w = nullptr;           // [P] folded weights (after finalize; export)
-  uint2 *d_post = nullptr;        // [P + 2] interleaved (doc id, weight bits): what the scoring kernel streams
+  uint2 *d_post = nullptr;        // [P + 68] interleaved (doc id, weight bits): what the scoring kernel streams
   float *d_dense = nullptr;       // [n_dense][dense_stride] weight columns of the densest terms
   int *d_dense_slot = nullptr;    // [n_terms] column index or -1
   uint32_t n_dense = 0, dense_stride = 0;
@@ -57,7 +57,7 @@ struct OiBm25 {
   u64 *d_gthr = nullptr;          // [max_batch]
   uint32_t *d_counter = nullptr;  // item counter
   u64 *d_lists = nullptr;         // [S][nq][k]
-  size_t lists_cap = 0;           // in (item) lists of max_k keys
+  size_t lists_cap = 0;           // in keys
   uint32_t *d_in_terms = nullptr; // staging of the host call's flat term array [max_batch * 64]
   uint32_t *d_in_offs = nullptr;  // [max_batch + 1]
 };
@@ -123,12 +123,13 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
 }
 
 #define OI_BM25_NONE 0xFFFFFFFFu
-#define OI_BM25_MAX_DENSE 16
+#define OI_BM25_MAX_DENSE 32
+#define OI_BM25_POST_PAD 68  // postings of 0xFF padding after the last list: a 64-posting chunk read from any cursor stays in bounds
 
 struct Bm25Params {
   const u64 *term_off;
   const uint32_t *doc_ids;
-  const uint2 *post;          // [P + 2] interleaved (doc id, folded weight bits)
+  const uint2 *post;          // [P + 68] interleaved (doc id, folded weight bits)
   const float *dense;         // [n_dense][dense_stride] weight columns of the densest terms (0 where absent)
   const int *dense_slot;      // [n_terms] column of a term, or -1
   uint32_t dense_stride;
@@ -145,6 +146,7 @@ struct Bm25Params {
   uint32_t S;                 // super-ranges
   uint32_t n_blocks;
   uint32_t ng;                // warps (= work items in flight) per CTA
+  uint32_t nslot;             // staged 64-posting chunks per warp (0 = no staging)
 };
 
 __device__ __forceinline__ uint4 ldg_post2(const uint2 *p) {
@@ -155,8 +157,11 @@ __device__ __forceinline__ uint4 ldg_post2(const uint2 *p) {
 // postings at a time (one 16-byte load = 2 postings per lane) from the 16-byte-aligned pair at or below the
 // cursor, adds every weight whose document is below `bend` to acc[], and stops at the first posting outside
 // the block.  *pos_out = the new cursor, *nxt_out = the document there (NONE at the end of the list).
+// `st` (warp-uniform, may be NULL) = this warp's staged copy of the first chunk: lane l's 16 bytes at st[l],
+// a bulk copy of the 512 bytes from exactly the address the first iteration would load.
 __device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 base, uint32_t pos, uint32_t end, uint32_t bbase,
-                                            uint32_t bend, float *acc, int lane, uint32_t *pos_out, uint32_t *nxt_out) {
+                                            uint32_t bend, float *acc, int lane, const uint4 *st, uint32_t *pos_out,
+                                            uint32_t *nxt_out) {
   // list-local 32-bit slot numbers over a 16-byte-aligned view of the list: slot j = posting (j - par)
   const uint32_t par = (uint32_t)(base & 1ull);
   const uint2 *lp = post + (base - par);
@@ -167,7 +172,8 @@ __device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 
   for (;;) {
     const uint32_t idx = a + 2u * (uint32_t)lane;
     uint4 v = make_uint4(OI_BM25_NONE, 0u, OI_BM25_NONE, 0u);
-    if (idx < jend) v = ldg_post2(lp + idx);     // the array is padded, so reading the pair is always in bounds
+    if (idx < jend) v = st ? st[lane] : ldg_post2(lp + idx);  // the array is padded: reading the pair is in bounds
+    st = nullptr;
     if (idx + 1 >= jend) v.z = OI_BM25_NONE;      // second slot belongs to the next list
     if (idx < j0) v.x = OI_BM25_NONE;             // leading slot below the cursor: skipped, not applied
     const bool in0 = v.x < bend, in1 = v.z < bend;
@@ -195,33 +201,144 @@ __device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 
   *nxt_out = nxt;
 }
 
-// A dense term: its weight column for the block is added to every document (0.0f where the term is absent,
-// which leaves a non-negative f32 sum bit-for-bit unchanged), 128-bit loads, 4 in flight per lane.
-__device__ __forceinline__ void dense_pass(const float *__restrict__ col, float *acc, uint32_t R, int lane) {
-  const float4 *c4 = reinterpret_cast<const float4 *>(col);
-  float4 *a4 = reinterpret_cast<float4 *>(acc);
-  for (uint32_t j0 = 0; j0 < R / 4; j0 += 128) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(c4 + j0 + 32 * u + lane);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float4 x = a4[j0 + 32 * u + lane];
-      x.x = x.x + v[u].x; x.y = x.y + v[u].y; x.z = x.z + v[u].z; x.w = x.w + v[u].w;
-      a4[j0 + 32 * u + lane] = x;
+// Dense terms: the weight column of the block is added to every document (0.0f where the term is absent, which
+// leaves a non-negative f32 sum bit-for-bit unchanged) with 128-bit loads; see block_passes.
+
+// One lane's share of the work item's term table: lane l of set 0 holds term l of the query (ascending term id),
+// lane l of set 1 holds term 32 + l.  Keeping the cursors in registers (instead of shared-memory arrays every lane
+// re-reads per term and per block) makes "which lists have postings in this block" one ballot, "next block with
+// any posting" one warp reduction, and lets the warp visit only the lists that are present.
+struct TermRegs {
+  u64 base;       // posting-array offset of the list
+  uint32_t cur;   // postings consumed so far
+  uint32_t end;   // list length
+  uint32_t nxt;   // document at the cursor (NONE = exhausted / no such term)
+  uint32_t den;   // dense column of the term (NONE = sparse)
+};
+
+__device__ __forceinline__ void term_setup(TermRegs &T, const Bm25Params &p, uint32_t q, uint32_t i, uint32_t nt, uint32_t doc0) {
+  T.base = 0; T.cur = 0; T.end = 0; T.nxt = OI_BM25_NONE; T.den = OI_BM25_NONE;
+  if (i >= nt) return;
+  const uint32_t t = p.qterms[(size_t)q * OI_BM25_MAX_QTERMS + i];
+  const u64 lo = p.term_off[t], hi = p.term_off[t + 1];
+  const int slot = p.dense_slot[t];
+  T.base = lo;
+  T.end = (uint32_t)(hi - lo);
+  if (slot >= 0) {  // dense terms touch every block
+    T.den = (uint32_t)slot;
+    T.nxt = doc0;
+  } else {          // one binary search positions the cursor at the super-range start
+    u64 a = lo, b = hi;
+    while (a < b) {
+      const u64 mid = a + ((b - a) >> 1);
+      if (__ldg(p.doc_ids + mid) < doc0) a = mid + 1; else b = mid;
     }
+    T.cur = (uint32_t)(a - lo);
+    T.nxt = a < hi ? __ldg(p.doc_ids + a) : OI_BM25_NONE;
+  }
+}
+
+// global -> shared bulk copy (TMA 1-D, SASS UBLKCP) without a cache hint: postings are re-read by the other queries
+__device__ __forceinline__ void bm25_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(oi_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(oi_smem_u32(bar))
+               : "memory");
+}
+
+// The term passes of one block for one register set, ascending term id (SPEC §3 order).  First every sparse list
+// with postings in the block gets its first 64-posting chunk requested -- lane i issues ONE bulk copy for term i,
+// all lists in flight at once, completion counted on the warp's mbarrier -- then the present lists are visited
+// in order: a dense term adds its column, a sparse term consumes its staged chunk (and, for a segment longer than
+// the chunk, goes on with direct loads).
+template <int DW>
+__device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, float *acc, uint4 *stage, void *mbar, uint32_t &phase,
+                                             uint32_t bbase, uint32_t bend, int lane) {
+  const bool present = T.nxt < bend;
+  const uint32_t pm = __ballot_sync(0xFFFFFFFFu, present);
+  if (pm == 0) return;
+  const uint32_t sm = __ballot_sync(0xFFFFFFFFu, present && T.den == OI_BM25_NONE);
+  const uint32_t n_sparse = (uint32_t)__popc(sm);
+  const uint32_t n_staged = min(n_sparse, p.nslot);
+  if (n_staged) {
+    if (lane == 0) oi_mbar_expect_tx(mbar, n_staged * 512u);
+    const uint32_t my_slot = (uint32_t)__popc(sm & ((1u << lane) - 1u));
+    if (((sm >> lane) & 1u) && my_slot < p.nslot) {
+      const uint32_t par = (uint32_t)(T.base & 1ull);
+      const uint32_t a = (T.cur + par) & ~1u;  // the 16-byte-aligned pair sparse_pass's first load starts from
+      bm25_bulk_g2s(stage + my_slot * 32u, p.post + (T.base - par) + a, 512u, mbar);  // the array is padded by 64 postings
+    }
+  }
+  bool waited = false;
+  uint32_t m = pm;
+  while (m) {
+    const int i = __ffs((int)m) - 1;
+    m &= m - 1u;
+    const uint32_t den = __shfl_sync(0xFFFFFFFFu, T.den, i);
+    if (den != OI_BM25_NONE) {
+      // a run of consecutive present dense terms is one stream of column rounds (32 * DW float4 each): the loads
+      // of the next round -- of this column or of the next term's -- are in flight while this round is added
+      const uint32_t rounds = p.R / (128u * DW);
+      int ti = i;
+      const float4 *c4 = reinterpret_cast<const float4 *>(p.dense + (size_t)den * p.dense_stride + bbase);
+      float4 *a4 = reinterpret_cast<float4 *>(acc);
+      float4 v[DW];
+#pragma unroll
+      for (int u = 0; u < DW; ++u) v[u] = __ldg(c4 + 32 * u + lane);
+      for (;;) {
+        int nx = -1;
+        if (m) {
+          const int cand = __ffs((int)m) - 1;
+          if (!((sm >> cand) & 1u)) nx = cand;  // the next present term is dense too
+        }
+        const float4 *cn = nullptr;
+        if (nx >= 0) cn = reinterpret_cast<const float4 *>(p.dense + (size_t)__shfl_sync(0xFFFFFFFFu, T.den, nx) * p.dense_stride + bbase);
+        for (uint32_t r = 0; r < rounds; ++r) {
+          const float4 *np = r + 1 < rounds ? c4 + (r + 1) * 32u * DW : cn;  // warp-uniform
+          float4 vn[DW];
+          if (np) {
+#pragma unroll
+            for (int u = 0; u < DW; ++u) vn[u] = __ldg(np + 32 * u + lane);
+          }
+#pragma unroll
+          for (int u = 0; u < DW; ++u) {
+            float4 x = a4[r * 32u * DW + 32 * u + lane];
+            x.x = x.x + v[u].x; x.y = x.y + v[u].y; x.z = x.z + v[u].z; x.w = x.w + v[u].w;
+            a4[r * 32u * DW + 32 * u + lane] = x;
+          }
+#pragma unroll
+          for (int u = 0; u < DW; ++u) v[u] = vn[u];
+        }
+        if (lane == ti) T.nxt = bend < p.n_docs ? bend : OI_BM25_NONE;
+        if (nx < 0) break;
+        __syncwarp();  // same lanes touch the same documents in every dense pass, but keep the passes ordered
+        m &= m - 1u;
+        ti = nx;
+        c4 = cn;
+      }
+    } else {
+      const u64 base = __shfl_sync(0xFFFFFFFFu, T.base, i);
+      const uint32_t cur = __shfl_sync(0xFFFFFFFFu, T.cur, i);
+      const uint32_t end = __shfl_sync(0xFFFFFFFFu, T.end, i);
+      const uint32_t slot = (uint32_t)__popc(sm & ((1u << i) - 1u));
+      const uint4 *sp = nullptr;
+      if (slot < n_staged) {
+        if (!waited) { oi_mbar_wait(mbar, phase); phase ^= 1u; waited = true; }
+        sp = stage + slot * 32u;
+      }
+      uint32_t pos_new, nxt;
+      sparse_pass(p.post, base, cur, end, bbase, bend, acc, lane, sp, &pos_new, &nxt);
+      if (lane == i) { T.cur = pos_new; T.nxt = nxt; }
+    }
+    __syncwarp();  // the next pass may touch the same documents
   }
 }
 
 // dynamic shared memory layout (per CTA, NG = warps per CTA):
-//   float acc[OI_BM25_ACC_FLOATS]            NG slices of R floats
-//   u64   cand[NG][cap]
-//   u64   tbase[NG][64]      posting-array offset of each term's list
-//   u32   tcur[NG][64]       cursor inside the list (postings consumed so far)
-//   u32   tend[NG][64]       list length
-//   u32   tnxt[NG][64]       doc id at the cursor (NONE = exhausted)
-//   u32   tden[NG][64]       dense column of the term (NONE = sparse)
+//   float  acc[NG][R]               block scores
+//   u64    cand[NG][cap]            candidate buffers
+//   uint4  stage[NG][nslot][32]     staged first chunks (64 postings each) of the block's sparse lists
 //   GrpCtl ctl[NG]
+//   u64    mbar[NG]                 one mbarrier per warp for its bulk copies
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params p) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -232,26 +349,24 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
   g.size = 32;
   g.bar = 0;
 
-  float *acc_all = reinterpret_cast<float *>(s_dyn);
-  u64 *cand_all = reinterpret_cast<u64 *>(s_dyn + sizeof(float) * (size_t)NG * p.R);
-  u64 *tbase_all = cand_all + (size_t)NG * p.cap;
-  uint32_t *tcur_all = reinterpret_cast<uint32_t *>(tbase_all + (size_t)NG * OI_BM25_MAX_QTERMS);
-  uint32_t *tend_all = tcur_all + NG * OI_BM25_MAX_QTERMS;
-  uint32_t *tnxt_all = tend_all + NG * OI_BM25_MAX_QTERMS;
-  uint32_t *tden_all = tnxt_all + NG * OI_BM25_MAX_QTERMS;
-  GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(tden_all + NG * OI_BM25_MAX_QTERMS);
-
   const uint32_t R = p.R;
-  float *acc = acc_all + (size_t)gi * R;
+  float *acc = reinterpret_cast<float *>(s_dyn) + (size_t)gi * R;
+  u64 *cand_all = reinterpret_cast<u64 *>(s_dyn + sizeof(float) * (size_t)NG * R);
   u64 *cand = cand_all + (size_t)gi * p.cap;
-  u64 *tbase = tbase_all + gi * OI_BM25_MAX_QTERMS;
-  uint32_t *tcur = tcur_all + gi * OI_BM25_MAX_QTERMS;
-  uint32_t *tend = tend_all + gi * OI_BM25_MAX_QTERMS;
-  uint32_t *tnxt = tnxt_all + gi * OI_BM25_MAX_QTERMS;
-  uint32_t *tden = tden_all + gi * OI_BM25_MAX_QTERMS;
+  uint4 *stage_all = reinterpret_cast<uint4 *>(cand_all + (size_t)NG * p.cap);
+  uint4 *stage = stage_all + (size_t)gi * p.nslot * 32;
+  GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(stage_all + (size_t)NG * p.nslot * 32);
   GrpCtl *ctl = ctl_all + gi;
+  u64 *mbar = reinterpret_cast<u64 *>(ctl_all + NG) + gi;  // NG x 24 bytes of control blocks keep 8-byte alignment
+  constexpr int DW = 4;  // dense-pass loads per lane per round (two rounds are live: the one being added and the next)
 
+  if (lane == 0) {
+    oi_mbar_init(mbar, 1);
+    oi_mbar_fence_init();
+  }
   for (uint32_t i = lane; i < R; i += 32) acc[i] = 0.0f;
+  __syncwarp();
+  uint32_t phase = 0;
   const uint32_t n_items = p.S * p.nq;
   const uint32_t k = p.k, cap = p.cap;
 
@@ -266,61 +381,29 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
     const uint32_t blk0 = s * p.J, blk1 = min(p.n_blocks, blk0 + p.J);
     const uint32_t doc0 = blk0 * R;
 
-    // ---- item set-up: one binary search per sparse term positions the cursor at the super-range start
-    for (uint32_t i = lane; i < nt; i += 32) {
-      const uint32_t t = p.qterms[(size_t)q * OI_BM25_MAX_QTERMS + i];
-      const u64 lo = p.term_off[t], hi = p.term_off[t + 1];
-      const int slot = p.dense_slot[t];
-      tbase[i] = lo;
-      tend[i] = (uint32_t)(hi - lo);
-      if (slot >= 0) {  // dense terms touch every block
-        tden[i] = (uint32_t)slot;
-        tcur[i] = 0;
-        tnxt[i] = doc0;
-      } else {
-        u64 a = lo, b = hi;
-        while (a < b) {
-          const u64 mid = a + ((b - a) >> 1);
-          if (__ldg(p.doc_ids + mid) < doc0) a = mid + 1; else b = mid;
-        }
-        tden[i] = OI_BM25_NONE;
-        tcur[i] = (uint32_t)(a - lo);
-        tnxt[i] = a < hi ? __ldg(p.doc_ids + a) : OI_BM25_NONE;
-      }
-    }
+    // ---- item set-up: lane l takes terms l and 32 + l of the query
+    TermRegs T0, T1;
+    term_setup(T0, p, q, (uint32_t)lane, nt, doc0);
+    term_setup(T1, p, q, 32u + (uint32_t)lane, nt, doc0);
     if (lane == 0) { ctl->cnt = 0; ctl->thr = 0ull; ctl->aux = 0; }
     __syncwarp();
 
     uint32_t blk = blk0;
     while (blk < blk1) {
       // ---- skip straight to the next block that holds a posting of any query term -------------
-      uint32_t mn = OI_BM25_NONE;
-      for (uint32_t i = lane; i < nt; i += 32) mn = min(mn, tnxt[i]);
-      mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+      const uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, min(T0.nxt, T1.nxt));
       if (mn == OI_BM25_NONE) break;
       blk = max(blk, mn >> p.r_shift);
       if (blk >= blk1) break;
       const uint32_t bbase = blk * R;
       const uint32_t bend = min(p.n_docs, bbase + R);
       ++blk;
-      // ---- term passes, ascending term id (SPEC §3 order); a pass never writes a document twice -----------
-      for (uint32_t i = 0; i < nt; ++i) {
-        if (tnxt[i] >= bend) continue;  // warp-uniform: the list has nothing in this block
-        const uint32_t slot = tden[i];
-        if (slot != OI_BM25_NONE) {
-          dense_pass(p.dense + (size_t)slot * p.dense_stride + bbase, acc, R, lane);
-          __syncwarp();
-          if (lane == 0) tnxt[i] = bend < p.n_docs ? bend : OI_BM25_NONE;
-        } else {
-          uint32_t pos_new, nxt;
-          sparse_pass(p.post, tbase[i], tcur[i], tend[i], bbase, bend, acc, lane, &pos_new, &nxt);
-          __syncwarp();
-          if (lane == 0) { tcur[i] = pos_new; tnxt[i] = nxt; }
-        }
-        __syncwarp();
-      }
+      // the grid-wide threshold is requested now and consumed after the passes
+      const u64 gthr_now = ld_relaxed_u64(p.gthr + q);
+      block_passes<DW>(T0, p, acc, stage, mbar, phase, bbase, bend, lane);
+      if (nt > 32) block_passes<DW>(T1, p, acc, stage, mbar, phase, bbase, bend, lane);
       // ---- selection: positive scores that beat the running threshold -------------------------
-      const u64 thr = max(ctl->thr, ld_relaxed_u64(p.gthr + q));
+      const u64 thr = max(ctl->thr, gthr_now);
       const float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
       __syncwarp();
       // one pass reads, tests and clears the block, 4 x 128 bits per lane per step.  In steady state only a
@@ -573,7 +656,12 @@ void oi_bm25_free(oi_index *h) {
   h->bm25 = nullptr;
 }
 
-static size_t bm25_lists_cap(const oi_index *h) { return (size_t)3 * h->num_sms * 24 + 64 + 2 * (size_t)h->desc.max_batch; }
+// capacity of the per-item list workspace in KEYS: the default schedule at k <= 128 (24 items per warp, up to 24 warps
+// per CTA) or two lists per query at max_k, whichever is larger; a call that would need more lowers its item count
+static size_t bm25_lists_cap(const oi_index *h) {
+  const size_t a = (size_t)24 * h->num_sms * 24 * 128, b = 2 * (size_t)h->desc.max_batch * h->desc.max_k;
+  return (a > b ? a : b) + 64 * (size_t)h->desc.max_k;
+}
 
 static oi_status bm25_alloc_workspace(oi_index *h, OiBm25 *b) {
   const size_t B = h->desc.max_batch;
@@ -582,7 +670,7 @@ static oi_status bm25_alloc_workspace(oi_index *h, OiBm25 *b) {
   BM_CK(cudaMalloc(&b->d_gthr, B * sizeof(u64)));
   BM_CK(cudaMalloc(&b->d_counter, sizeof(uint32_t)));
   b->lists_cap = bm25_lists_cap(h);
-  BM_CK(cudaMalloc(&b->d_lists, b->lists_cap * h->desc.max_k * sizeof(u64)));
+  BM_CK(cudaMalloc(&b->d_lists, b->lists_cap * sizeof(u64)));
   BM_CK(cudaMalloc(&b->d_in_terms, B * OI_BM25_MAX_QTERMS * sizeof(uint32_t)));
   BM_CK(cudaMalloc(&b->d_in_offs, (B + 1) * sizeof(uint32_t)));
   return OI_OK;
@@ -787,14 +875,17 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
     const double d = (double)df[t];
     idf[t] = df[t] == 0 ? 0.0f : (float)std::log(1.0 + ((double)N - d + 0.5) / (d + 0.5));
   }
-  // dense columns: the terms present in at least a quarter of this shard's documents (at most 16, densest first)
+  // dense columns: the terms present in at least 1/16 of this shard's documents (at most 32, densest first).  At that
+  // density a 1024-document block holds >= 64 postings of the term -- a whole chunk -- so streaming the 4-byte column
+  // costs no more instructions than walking the 8-byte postings and exposes one load latency instead of several.
   std::vector<int> slot(b->n_terms, -1);
   {
     std::vector<u64> off((size_t)b->n_terms + 1);
     BM_CK(cudaMemcpyAsync(off.data(), b->d_term_off, off.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
     BM_CK(cudaStreamSynchronize(st));
     std::vector<std::pair<u64, uint32_t>> heavy;
-    const u64 min_df = std::max<u64>((u64)h->desc.n_docs / 4, 1024);
+    const u64 div = h->bm25_dense_div > 0 ? (u64)h->bm25_dense_div : 16;
+    const u64 min_df = std::max<u64>((u64)h->desc.n_docs / div, 1024);
     for (uint32_t t = 0; t < b->n_terms; ++t)
       if (off[t + 1] - off[t] >= min_df) heavy.push_back({off[t + 1] - off[t], t});
     std::sort(heavy.begin(), heavy.end(), [](const std::pair<u64, uint32_t> &x, const std::pair<u64, uint32_t> &y) { return x.first > y.first; });
@@ -807,10 +898,10 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
   cudaFree(b->d_post); cudaFree(b->d_dense); cudaFree(b->d_dense_slot);
   b->d_post = nullptr; b->d_dense = nullptr; b->d_dense_slot = nullptr;
   const size_t dense_elems = (size_t)std::max<uint32_t>(b->n_dense, 1) * b->dense_stride;
-  BM_CK(cudaMalloc(&b->d_post, ((size_t)b->n_postings + 2) * sizeof(uint2)));
+  BM_CK(cudaMalloc(&b->d_post, ((size_t)b->n_postings + OI_BM25_POST_PAD) * sizeof(uint2)));
   BM_CK(cudaMalloc(&b->d_dense, std::max<size_t>(dense_elems, 4) * sizeof(float)));
   BM_CK(cudaMalloc(&b->d_dense_slot, (size_t)b->n_terms * sizeof(int)));
-  BM_CK(cudaMemsetAsync(b->d_post, 0xFF, ((size_t)b->n_postings + 2) * sizeof(uint2), st));
+  BM_CK(cudaMemsetAsync(b->d_post, 0xFF, ((size_t)b->n_postings + OI_BM25_POST_PAD) * sizeof(uint2), st));
   BM_CK(cudaMemsetAsync(b->d_dense, 0, std::max<size_t>(dense_elems, 4) * sizeof(float), st));
   BM_CK(cudaMemcpyAsync(b->d_dense_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   float *d_idf = nullptr;
@@ -873,33 +964,49 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   uint32_t cap = 256;
   while (cap < 2 * k) cap <<= 1;
   p.cap = cap;
-  // one warp per work item.  k <= 128: 24 warps per CTA, 1024-document blocks (more warps in flight hide the
-  // L2 latency of the posting loads); larger k: 16 / 8 / 4 warps with 2048 / 4096 / 8192-document blocks,
-  // as many as 64 KB of candidate buffers allow.
+  // one warp per work item.  k <= 128: 16 warps per CTA with 2048-document blocks and 8 staged chunks per warp
+  // (224 KB of shared memory); larger k: 8 / 4 / 2 warps with 4096 / 8192 / 16384-document blocks, as many as 64 KB
+  // of candidate buffers allow.
+  // Tuning options (oi_index_set_option): bm25_warps, bm25_block_docs, bm25_stage_slots; bm25_variant 1..15 keeps
+  // its old meaning (warps per CTA rounded down to a power of two, 32768 / warps documents per block).
+  const size_t smem_max = 227 * 1024;
+  auto smem_for = [&](uint32_t ng_, uint32_t R_, uint32_t ns_) {
+    return sizeof(float) * (size_t)ng_ * R_ + (size_t)ng_ * cap * sizeof(u64) + (size_t)ng_ * ns_ * 512 +
+           (size_t)ng_ * (sizeof(GrpCtl) + sizeof(u64));
+  };
   uint32_t ng = 16;
   while (ng > 1 && ng * cap > 8192) ng >>= 1;
   p.R = OI_BM25_ACC_FLOATS / ng;
-  if (cap <= 256 && h->bm25_variant != 16) { ng = 24; p.R = 1024; }
-  if (h->bm25_variant >= 1 && h->bm25_variant <= 15) {  // tuning override: warps per CTA (power of two)
+  if (h->bm25_variant >= 1 && h->bm25_variant <= 15) {
     uint32_t f = 1;
     while (f * 2 <= (uint32_t)h->bm25_variant) f <<= 1;
     if (f * cap <= 8192) { ng = f; p.R = OI_BM25_ACC_FLOATS / ng; }
   }
+  if (h->bm25_warps > 0) ng = (uint32_t)h->bm25_warps;
+  if (h->bm25_block_docs > 0) p.R = (uint32_t)h->bm25_block_docs;
+  if (ng > 24 || p.R < 1024 || (p.R & (p.R - 1)) || smem_for(ng, p.R, 0) > smem_max)
+    return h->fail(OI_ERR_INVALID_ARG, "BM25 tuning: %u warps x %u-document blocks (k = %u) do not fit one SM", ng, p.R, k);
+  uint32_t nslot = h->bm25_stage_slots >= 0 ? (uint32_t)h->bm25_stage_slots : 8;
+  while (nslot > 0 && smem_for(ng, p.R, nslot) > smem_max) --nslot;
+  p.nslot = nslot;
   p.ng = ng;
   p.r_shift = 0;
   while ((1u << p.r_shift) < p.R) ++p.r_shift;
   p.n_blocks = (p.n_docs + p.R - 1) / p.R;
   if (p.n_blocks == 0) p.n_blocks = 1;
   const uint32_t groups = (uint32_t)h->num_sms * ng;
-  uint32_t S = (3 * groups + nq - 1) / nq;
+  // super-ranges per query: enough work items (S x nq) for every warp to take ~24, so that the last items to finish
+  // (queries differ a lot in cost: zero to several dense terms) leave the SMs idle for a small part of the launch
+  const uint32_t ipw = h->bm25_items_per_warp > 0 ? (uint32_t)h->bm25_items_per_warp : 24;
+  uint32_t S = (ipw * groups + nq - 1) / nq;
   if (S < 1) S = 1;
   if (S > 512) S = 512;  // the per-query merge handles up to 512 sorted lists on its fast path
+  while (S > 1 && (size_t)S * nq * k > b->lists_cap) --S;
   if (S > p.n_blocks) S = p.n_blocks;
   p.J = (p.n_blocks + S - 1) / S;
   p.S = (p.n_blocks + p.J - 1) / p.J;
-  if ((size_t)p.S * nq > b->lists_cap) return h->fail(OI_ERR_CUDA, "internal: BM25 list workspace too small (%u x %u)", p.S, nq);
-  const size_t smem = sizeof(float) * (size_t)ng * p.R + (size_t)ng * cap * sizeof(u64) +
-                      (size_t)ng * OI_BM25_MAX_QTERMS * (sizeof(u64) + 4 * sizeof(uint32_t)) + ng * sizeof(GrpCtl);
+  if ((size_t)p.S * nq * k > b->lists_cap) return h->fail(OI_ERR_CUDA, "internal: BM25 list workspace too small (%u x %u)", p.S, nq);
+  const size_t smem = smem_for(ng, p.R, nslot);
   BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   uint32_t grid = (uint32_t)h->num_sms;

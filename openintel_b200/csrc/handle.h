@@ -41,6 +41,11 @@ struct oi_index {
   // BM25
   OiBm25 *bm25 = nullptr;
   int bm25_variant = 0;
+  int bm25_warps = 0;         // tuning: warps per CTA (0 = default)
+  int bm25_block_docs = 0;    // tuning: documents per block, a power of two >= 1024 (0 = default)
+  int bm25_dense_div = 0;     // tuning (before finalize): a term in >= n_docs / div documents gets a dense column (0 = default 16)
+  int bm25_items_per_warp = 0; // tuning: work items per warp the super-range count aims for (0 = default 24)
+  int bm25_stage_slots = -1;  // tuning: staged 64-posting chunks per warp (-1 = default, 0 = none)
 
   // multi-GPU
   OiComm *comm = nullptr;

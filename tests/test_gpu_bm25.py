@@ -68,6 +68,26 @@ def test_bm25_parity_bit_exact(oi, n, vocab, k, nq, groups):
             assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
 
 
+@pytest.mark.parametrize("warps,block_docs,slots", [(16, 1024, 8), (24, 1024, 0), (8, 2048, 3), (16, 1024, 1), (20, 1024, 2), (3, 4096, 16)])
+def test_bm25_tuning_options_bit_exact(oi, warps, block_docs, slots):
+    """warps per CTA, documents per block and staged chunks per warp change the schedule, never the result"""
+    n, vocab, k, nq = 60000, 2500, 100, 33
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = _weights(corp, n)
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=nq) as ix:
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.bm25_finalize()
+        ix.set_option("bm25_warps", warps)
+        ix.set_option("bm25_block_docs", block_docs)
+        ix.set_option("bm25_stage_slots", slots)
+        for uniform in (False, True):
+            qs = O.synth_query_terms(nq, 12, corp["cdf"], uniform=uniform)
+            ids, sc = ix.search_bm25(qs, k)
+            wi, ws = _oracle_lists(corp, w, qs, n, k)
+            assert np.array_equal(ids, wi)
+            assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
+
+
 @pytest.mark.parametrize("n,vocab,k,nq", [(30000, 800, 100, 20), (70000, 20000, 10, 5), (9000, 2000, 1000, 2)])
 def test_bm25_sparse_only_path_bit_exact(oi, n, vocab, k, nq):
     """bm25_variant = 100 builds no dense weight columns: every term, however common, walks its postings"""

@@ -47,8 +47,14 @@ def bench_bm25(a):
     df, sdl, npost = ix.bm25_local_stats()
     if a.groups:
         ix.set_option("bm25_variant", a.groups)
+    if a.warps:
+        ix.set_option("bm25_warps", a.warps)
+    if a.block_docs:
+        ix.set_option("bm25_block_docs", a.block_docs)
+    if a.slots >= 0:
+        ix.set_option("bm25_stage_slots", a.slots)
     stream = torch.cuda.current_stream().cuda_stream
-    for name, uniform in (("zipf", False), ("uniform", True)):
+    for name, uniform in (("zipf", False), ("uniform", True))[:1 if a.zipf_only else 2]:
         n_pool = 4
         pools = [O.synth_query_terms(a.batch, 8, cdf, uniform=uniform, first=p * a.batch) for p in range(n_pool)]
         touched = float(np.mean([df[p].astype(np.int64).sum(axis=1).mean() for p in pools]))
@@ -152,6 +158,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--groups", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0, help="bm25_warps tuning option")
+    ap.add_argument("--block-docs", type=int, default=0, help="bm25_block_docs tuning option")
+    ap.add_argument("--slots", type=int, default=-1, help="bm25_stage_slots tuning option")
+    ap.add_argument("--zipf-only", action="store_true")
     ap.add_argument("--debug", type=int, default=0)
     a = ap.parse_args()
     if a.workload == "gemm":
