@@ -250,9 +250,42 @@ __device__ __forceinline__ void bm25_bulk_g2s(void *smem_dst, const void *gmem_s
 // all lists in flight at once, completion counted on the warp's mbarrier -- then the present lists are visited
 // in order: a dense term adds its column, a sparse term consumes its staged chunk (and, for a segment longer than
 // the chunk, goes on with direct loads).
-template <int DW>
+// One or two dense columns in one sweep over the block's scores: x = (FRESH ? 0 : acc) + a (+ b), ascending term
+// order, 4 x 128 bits per column and lane in flight.  FRESH = no pass has written acc[] for this block yet: the
+// sweep then only stores (0.0f + w == w for every weight, bit for bit), so the block needs no clearing pass.
+template <bool FRESH, int NC>
+__device__ __forceinline__ void dense_sweep(const float4 *__restrict__ c0, const float4 *__restrict__ c1, float4 *a4, uint32_t R, int lane) {
+#pragma unroll 2
+  for (uint32_t j0 = 0; j0 < R / 4; j0 += 128) {
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      va[u] = __ldg(c0 + j0 + 32 * u + lane);
+      if (NC == 2) vb[u] = __ldg(c1 + j0 + 32 * u + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float4 x = va[u];
+      if (!FRESH) {
+        const float4 o = a4[j0 + 32 * u + lane];
+        x.x = o.x + x.x; x.y = o.y + x.y; x.z = o.z + x.z; x.w = o.w + x.w;
+      }
+      if (NC == 2) { x.x = x.x + vb[u].x; x.y = x.y + vb[u].y; x.z = x.z + vb[u].z; x.w = x.w + vb[u].w; }
+      a4[j0 + 32 * u + lane] = x;
+    }
+  }
+}
+
+// The term passes of one block for one register set, ascending term id (SPEC §3 order).  First every sparse list
+// with postings in the block gets its first 64-posting chunk requested -- lane i issues ONE bulk copy for term i,
+// all lists in flight at once, completion counted on the warp's mbarrier -- then the present lists are visited
+// in order: dense terms add their columns (two consecutive ones share a sweep), a sparse term consumes its staged
+// chunk (and, for a segment longer than the chunk, goes on with direct loads).  `fresh` = acc[] holds nothing for
+// this block yet: a dense first pass overwrites it, a sparse first pass clears it first.
+template <uint32_t RT>
 __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, float *acc, uint4 *stage, void *mbar, uint32_t &phase,
-                                             uint32_t bbase, uint32_t bend, int lane) {
+                                             bool &fresh, uint32_t bbase, uint32_t bend, int lane) {
+  const uint32_t R = RT ? RT : p.R;
   const bool present = T.nxt < bend;
   const uint32_t pm = __ballot_sync(0xFFFFFFFFu, present);
   if (pm == 0) return;
@@ -268,6 +301,8 @@ __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, f
       bm25_bulk_g2s(stage + my_slot * 32u, p.post + (T.base - par) + a, 512u, mbar);  // the array is padded by 64 postings
     }
   }
+  float4 *a4 = reinterpret_cast<float4 *>(acc);
+  const uint32_t nxt_dense = bend < p.n_docs ? bend : OI_BM25_NONE;  // a dense term is present in every block
   bool waited = false;
   uint32_t m = pm;
   while (m) {
@@ -275,47 +310,32 @@ __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, f
     m &= m - 1u;
     const uint32_t den = __shfl_sync(0xFFFFFFFFu, T.den, i);
     if (den != OI_BM25_NONE) {
-      // a run of consecutive present dense terms is one stream of column rounds (32 * DW float4 each): the loads
-      // of the next round -- of this column or of the next term's -- are in flight while this round is added
-      const uint32_t rounds = p.R / (128u * DW);
-      int ti = i;
-      const float4 *c4 = reinterpret_cast<const float4 *>(p.dense + (size_t)den * p.dense_stride + bbase);
-      float4 *a4 = reinterpret_cast<float4 *>(acc);
-      float4 v[DW];
-#pragma unroll
-      for (int u = 0; u < DW; ++u) v[u] = __ldg(c4 + 32 * u + lane);
-      for (;;) {
-        int nx = -1;
-        if (m) {
-          const int cand = __ffs((int)m) - 1;
-          if (!((sm >> cand) & 1u)) nx = cand;  // the next present term is dense too
-        }
-        const float4 *cn = nullptr;
-        if (nx >= 0) cn = reinterpret_cast<const float4 *>(p.dense + (size_t)__shfl_sync(0xFFFFFFFFu, T.den, nx) * p.dense_stride + bbase);
-        for (uint32_t r = 0; r < rounds; ++r) {
-          const float4 *np = r + 1 < rounds ? c4 + (r + 1) * 32u * DW : cn;  // warp-uniform
-          float4 vn[DW];
-          if (np) {
-#pragma unroll
-            for (int u = 0; u < DW; ++u) vn[u] = __ldg(np + 32 * u + lane);
-          }
-#pragma unroll
-          for (int u = 0; u < DW; ++u) {
-            float4 x = a4[r * 32u * DW + 32 * u + lane];
-            x.x = x.x + v[u].x; x.y = x.y + v[u].y; x.z = x.z + v[u].z; x.w = x.w + v[u].w;
-            a4[r * 32u * DW + 32 * u + lane] = x;
-          }
-#pragma unroll
-          for (int u = 0; u < DW; ++u) v[u] = vn[u];
-        }
-        if (lane == ti) T.nxt = bend < p.n_docs ? bend : OI_BM25_NONE;
-        if (nx < 0) break;
-        __syncwarp();  // same lanes touch the same documents in every dense pass, but keep the passes ordered
-        m &= m - 1u;
-        ti = nx;
-        c4 = cn;
+      const float4 *c0 = reinterpret_cast<const float4 *>(p.dense + (size_t)den * p.dense_stride + bbase);
+      int i2 = -1;
+      if (m) {
+        const int cand = __ffs((int)m) - 1;
+        if (!((sm >> cand) & 1u)) i2 = cand;  // the next present term is dense too: one sweep adds both columns
       }
+      if (i2 >= 0) {
+        m &= m - 1u;
+        const uint32_t den2 = __shfl_sync(0xFFFFFFFFu, T.den, i2);
+        const float4 *c1 = reinterpret_cast<const float4 *>(p.dense + (size_t)den2 * p.dense_stride + bbase);
+        if (fresh) dense_sweep<true, 2>(c0, c1, a4, R, lane);
+        else dense_sweep<false, 2>(c0, c1, a4, R, lane);
+      } else {
+        if (fresh) dense_sweep<true, 1>(c0, c0, a4, R, lane);
+        else dense_sweep<false, 1>(c0, c0, a4, R, lane);
+      }
+      fresh = false;
+      if (lane == i || lane == i2) T.nxt = nxt_dense;
     } else {
+      if (fresh) {  // a sparse first pass scatters into the block: clear it first
+        const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 4
+        for (uint32_t j = lane; j < R / 4; j += 32) a4[j] = zero4;
+        fresh = false;
+        __syncwarp();
+      }
       const u64 base = __shfl_sync(0xFFFFFFFFu, T.base, i);
       const uint32_t cur = __shfl_sync(0xFFFFFFFFu, T.cur, i);
       const uint32_t end = __shfl_sync(0xFFFFFFFFu, T.end, i);
@@ -339,7 +359,7 @@ __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, f
 //   uint4  stage[NG][nslot][32]     staged first chunks (64 postings each) of the block's sparse lists
 //   GrpCtl ctl[NG]
 //   u64    mbar[NG]                 one mbarrier per warp for its bulk copies
-template <int MAXT>
+template <int MAXT, uint32_t RT>  // RT = documents per block at compile time (0 = p.R)
 __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params p) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int NG = (int)p.ng;
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
   g.size = 32;
   g.bar = 0;
 
-  const uint32_t R = p.R;
+  const uint32_t R = RT ? RT : p.R;
   float *acc = reinterpret_cast<float *>(s_dyn) + (size_t)gi * R;
   u64 *cand_all = reinterpret_cast<u64 *>(s_dyn + sizeof(float) * (size_t)NG * R);
   u64 *cand = cand_all + (size_t)gi * p.cap;
@@ -358,13 +378,11 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
   GrpCtl *ctl_all = reinterpret_cast<GrpCtl *>(stage_all + (size_t)NG * p.nslot * 32);
   GrpCtl *ctl = ctl_all + gi;
   u64 *mbar = reinterpret_cast<u64 *>(ctl_all + NG) + gi;  // NG x 24 bytes of control blocks keep 8-byte alignment
-  constexpr int DW = 4;  // dense-pass loads per lane per round (two rounds are live: the one being added and the next)
 
   if (lane == 0) {
     oi_mbar_init(mbar, 1);
     oi_mbar_fence_init();
   }
-  for (uint32_t i = lane; i < R; i += 32) acc[i] = 0.0f;
   __syncwarp();
   uint32_t phase = 0;
   const uint32_t n_items = p.S * p.nq;
@@ -400,23 +418,22 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
       ++blk;
       // the grid-wide threshold is requested now and consumed after the passes
       const u64 gthr_now = ld_relaxed_u64(p.gthr + q);
-      block_passes<DW>(T0, p, acc, stage, mbar, phase, bbase, bend, lane);
-      if (nt > 32) block_passes<DW>(T1, p, acc, stage, mbar, phase, bbase, bend, lane);
+      bool fresh = true;  // acc[] holds the previous block's scores until the first pass overwrites or clears it
+      block_passes<RT>(T0, p, acc, stage, mbar, phase, fresh, bbase, bend, lane);
+      if (nt > 32) block_passes<RT>(T1, p, acc, stage, mbar, phase, fresh, bbase, bend, lane);
       // ---- selection: positive scores that beat the running threshold -------------------------
       const u64 thr = max(ctl->thr, gthr_now);
       const float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
       __syncwarp();
-      // one pass reads, tests and clears the block, 4 x 128 bits per lane per step.  In steady state only a
-      // handful of scores survive the threshold; a survivor that finds the buffer full is written back, so
-      // the (rare) overflow path below sees exactly the scores that still have to be ranked.
+      // one pass reads and tests the block, 4 x 128 bits per lane per step (the next block's first pass overwrites
+      // or clears acc[]).  In steady state only a handful of scores survive the threshold; a group with a survivor
+      // that finds the buffer full is rewritten with only the scores still to be ranked, for the overflow path.
       float4 *accw = reinterpret_cast<float4 *>(acc);
-      const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 2
       for (uint32_t jb = 0; jb < R / 4; jb += 128) {
         float4 vv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) vv[u] = accw[jb + 32 * u + lane];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) accw[jb + 32 * u + lane] = zero4;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float4 v = vv[u];
@@ -425,7 +442,6 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
             const uint32_t j = jb + 32 * u + lane;
             const float sc4[4] = {v.x, v.y, v.z, v.w};
             float back[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            bool any_back = false;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               if (sc4[c4] > 0.0f && sc4[c4] >= tsc) {
@@ -433,18 +449,19 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
                 if (key > thr) {
                   const uint32_t at = atomicAdd(&ctl->cnt, 1u);
                   if (at < cap) cand[at] = key;
-                  else { back[c4] = sc4[c4]; any_back = true; }
+                  else back[c4] = sc4[c4];
                 }
               }
             }
-            if (any_back) accw[j] = make_float4(back[0], back[1], back[2], back[3]);
+            accw[j] = make_float4(back[0], back[1], back[2], back[3]);  // only the scores that did not fit stay
           }
         }
       }
       __syncwarp();
       if (ctl->cnt > cap) {
-        // overflow (cold threshold): the buffer holds `cap` valid keys and the scores that did not fit are
-        // back in acc[]; rank those in spans that cannot overflow the buffer, compacting between spans
+        // overflow (cold threshold): the buffer holds `cap` valid keys; of the scores that can still matter, acc[]
+        // holds exactly those that did not fit (everything else left there is below the threshold and fails the
+        // key test again); rank them in spans that cannot overflow the buffer, compacting between spans
         __syncwarp();
         if (lane == 0) ctl->cnt = cap;
         __syncwarp();
@@ -470,7 +487,6 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
             if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
           }
         }
-        for (uint32_t j = lane; j < R / 4; j += 32) accw[j] = zero4;  // the written-back scores are ranked now
       } else if (ctl->cnt > cap / 2) {
         grp_compact(cand, ctl, cap, k, g);
         if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
@@ -1007,13 +1023,15 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   p.S = (p.n_blocks + p.J - 1) / p.J;
   if ((size_t)p.S * nq * k > b->lists_cap) return h->fail(OI_ERR_CUDA, "internal: BM25 list workspace too small (%u x %u)", p.S, nq);
   const size_t smem = smem_for(ng, p.R, nslot);
-  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   uint32_t grid = (uint32_t)h->num_sms;
   const uint32_t ctas_useful = (p.S * nq + ng - 1) / ng;
   if (grid > ctas_useful) grid = ctas_useful;
-  if (ng > 16) bm25_blocked_kernel<768><<<grid, ng * 32, smem, st>>>(p);
-  else bm25_blocked_kernel<512><<<grid, ng * 32, smem, st>>>(p);
+  if (ng > 16) bm25_blocked_kernel<768, 0><<<grid, ng * 32, smem, st>>>(p);
+  else if (p.R == 2048) bm25_blocked_kernel<512, 2048><<<grid, ng * 32, smem, st>>>(p);
+  else bm25_blocked_kernel<512, 0><<<grid, ng * 32, smem, st>>>(p);
   ++h->launches;
   BM_CK(cudaGetLastError());
   BM_CK(oi_launch_merge_shards(b->d_lists, p.S, nq, k, d_out_keys, st, &h->launches));
