@@ -168,6 +168,10 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->gemm_sample_tiles = (int)value;
     return OI_OK;
   }
+  if (!strcmp(name, "comm_debug_skip_gather")) {
+    h->comm_skip = (int)value;
+    return OI_OK;
+  }
   if (!strcmp(name, "bm25_variant")) {
     h->bm25_variant = (int)value;
     return OI_OK;

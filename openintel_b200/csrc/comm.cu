@@ -115,7 +115,7 @@ oi_status oi_comm_gather_merge(oi_index *h, const u64 *d_local, uint32_t nq, uin
   if (nq == 0) return OI_OK;
   OiNcclApi *api = nccl_api();
   if (!h->comm || !api->lib) return h->fail(OI_ERR_STATE, "oi_index_comm_init was not called");
-  ncclResult_t r = api->AllGather(d_local, h->d_gather, (size_t)nq * k, ncclUint64, h->comm->comm, st);
+  ncclResult_t r = h->comm_skip ? ncclSuccess : api->AllGather(d_local, h->d_gather, (size_t)nq * k, ncclUint64, h->comm->comm, st);
   if (r != ncclSuccess) return h->fail(OI_ERR_COMM, "ncclAllGather: %s", api->GetErrorString(r));
   cudaError_t e = oi_launch_merge_shards(h->d_gather, (uint32_t)h->world, nq, k, d_out, st, &h->launches);
   if (e != cudaSuccess) return h->fail(OI_ERR_CUDA, "merge_shards: %s", cudaGetErrorString(e));

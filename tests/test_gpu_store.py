@@ -1,0 +1,89 @@
+"""BASELINE.json configs[0] end to end on the GPU: 10k synthetic posts in a SQLite store, 384-dim f32 embeddings,
+BM25 + cosine + RRF top-10 for a single query.  The index is lifted out of the store by openintel_b200.store
+(reference tokenizer -> CSR -> C ABI) and the answer is compared with the CPU oracle run on an independent
+restatement of the same lift (oracle tokenizer + plain Python CSR): BM25 and RRF bit-exact, cosine within the
+f32 tolerance of SPEC §2.  Self-written oracle: the reference has no retrieval code."""
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+
+import oracle as O
+from gpu_util import assert_ranked_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oi():
+    import __graft_entry__ as ge  # noqa: F401
+    import openintel_b200
+    openintel_b200.load_library()
+    import runpy
+    from openintel_b200 import hostlib
+    runpy.run_path(os.path.join(os.path.dirname(hostlib.__file__), "host", "build.py"), run_name="__build__")
+    return openintel_b200
+
+
+def _python_csr(texts):
+    docs = [O.tokenize(t) for t in texts]
+    vocab = sorted({w for d in docs for w in d})
+    tid = {w: i for i, w in enumerate(vocab)}
+    lists = [[] for _ in vocab]
+    for d, toks in enumerate(docs):
+        for w, tf in sorted(Counter(toks).items()):
+            lists[tid[w]].append((d, tf))
+    off = np.zeros(len(vocab) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(l) for l in lists])
+    di = np.array([d for l in lists for d, _ in l], dtype=np.uint32)
+    tf = np.array([f for l in lists for _, f in l], dtype=np.uint32)
+    dl = np.array([len(d) for d in docs], dtype=np.uint32)
+    return tid, off, di, tf, dl
+
+
+@pytest.mark.parametrize("n,vocab,dim,k", [(10000, 50000, 384, 10), (3000, 500, 64, 100)])
+def test_store_hybrid_matches_oracle(oi, tmp_path, n, vocab, dim, k):
+    from openintel_b200 import store
+    posts, _ = store.synth_posts(n, vocab, O.SEED, O)
+    emb = O.synth_rows_f32(n, dim) * np.float32(3.5)  # un-normalised in the store: the lift normalises
+    conn = store.open_store(str(tmp_path / "posts.db"), dim=dim)
+    store.insert_posts(conn, posts, emb)
+    # queries: words taken from documents (mixed case / punctuation), one unknown word, and a duplicate
+    texts = ["%s %s, $%s zzzunknown %s" % tuple(posts[37]["text"].split()[:3] + [posts[37]["text"].split()[0]]),
+             " ".join(posts[n // 2]["text"].split()[:8]),
+             "nothingmatches here"]
+    qv = O.synth_rows_f32(len(texts), dim, stream=1) * np.float32(0.25)
+    with store.StoreIndex(conn, max_k=k, max_batch=4) as sx:
+        assert sx.n_docs == n
+        got = sx.search(texts, qv, k)
+        one = sx.search(texts[:1], qv[:1], k)  # the single-query call of configs[0]
+        q_terms = sx.query_terms(texts)
+        terms_words = [[sx.builder.term(int(t)) for t in q] for q in q_terms]
+    assert one[0] == got[0]
+    # ---- oracle on an independent restatement of the lift
+    tid, off, di, tf, dl = _python_csr([store.parse_post_text(p["text"]) for p in posts])
+    w = O.bm25_weights(off, di, tf, dl, O.bm25_idf(n, np.diff(off)))
+    rows = store.normalise_rows_f32(emb)
+    qn = store.normalise_rows_f32(qv)
+    for j, text in enumerate(texts):
+        want_terms = [tid[t] for t in O.tokenize(text) if t in tid]
+        assert [tid[x] for x in terms_words[j]] == want_terms
+        cs = O.cosine_scores_f32(rows, qn[j])
+        c_ids, c_sc, _ = O.topk_f64(cs, k)
+        s = O.bm25_score_dense(off, di, w, np.asarray(want_terms, dtype=np.uint32), n)
+        b_ids, _, _ = O.topk_f32(s, k, only_positive=True)
+        e_ids, e_val, e_rc, e_rb, m = O.rrf(c_ids, b_ids, k)
+        hits = got[j]
+        assert len(hits) == m
+        # cosine ranks may swap inside the f32 tie band (SPEC §2); when they do not, everything is identical
+        g_ids = np.array([h["doc_id"] for h in hits], dtype=np.uint32)
+        if np.array_equal(g_ids, e_ids[:m]):
+            assert np.array_equal(np.array([h["rrf"] for h in hits], dtype=np.float32).view(np.uint32), e_val[:m].view(np.uint32))
+            assert [h["rank_cosine"] for h in hits] == e_rc[:m].tolist() and [h["rank_bm25"] for h in hits] == e_rb[:m].tolist()
+        else:  # a tie-band swap in the cosine list: same set of fused documents
+            assert sorted(g_ids.tolist()) == sorted(e_ids[:m].tolist())
+        assert [h["id"] for h in hits] == ["post-%d" % d for d in g_ids]
+        if j == 2:
+            assert all(h["rank_bm25"] == 0 for h in hits)  # no known term: the fused list is the cosine list
+    conn.close()
