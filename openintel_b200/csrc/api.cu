@@ -196,6 +196,10 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->bm25_items_per_warp = (int)value;
     return OI_OK;
   }
+  if (!strcmp(name, "bm25_no_cold_bound")) {
+    h->bm25_no_cold_bound = (int)value;
+    return OI_OK;
+  }
   if (!strcmp(name, "bm25_stage_slots")) {
     OI_REQUIRE(value >= -1 && value <= 16, "bm25_stage_slots must be in -1..16 (-1 = default)");
     h->bm25_stage_slots = (int)value;

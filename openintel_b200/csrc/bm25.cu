@@ -147,6 +147,7 @@ struct Bm25Params {
   uint32_t n_blocks;
   uint32_t ng;                // warps (= work items in flight) per CTA
   uint32_t nslot;             // staged 64-posting chunks per warp (0 = no staging)
+  uint32_t cold_bound;        // 1: k <= 256 and the staging buffer can hold 256 group maxima (cold-start bound)
 };
 
 __device__ __forceinline__ uint4 ldg_post2(const uint2 *p) {
@@ -423,8 +424,43 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
       if (nt > 32) block_passes<RT>(T1, p, acc, stage, mbar, phase, fresh, bbase, bend, lane);
       // ---- selection: positive scores that beat the running threshold -------------------------
       const u64 thr = max(ctl->thr, gthr_now);
-      const float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
+      float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
       __syncwarp();
+      if (thr == 0ull && p.cold_bound) {
+        // cold start (no threshold yet: the first block of an item whose query has none either, i.e. every block of a
+        // single-query call): without a bound every positive score is a candidate and the buffer is sorted a dozen
+        // times.  The k-th largest of the block's 256 group maxima (groups of R / 256 documents) is a score at
+        // least k documents of the block reach, so nothing below it can be in the top k: one sort of 256 values
+        // replaces the repeated compactions.  The staging buffer is idle here and serves as scratch.
+        uint32_t *gm = reinterpret_cast<uint32_t *>(stage);
+        const float4 *accr = reinterpret_cast<const float4 *>(acc);
+        const uint32_t per_group = R / 1024u;  // float4s per group and lane: lane l owns float4s l, l + 32, ...
+#pragma unroll
+        for (uint32_t gi8 = 0; gi8 < 8; ++gi8) {
+          float mx = 0.0f;
+          for (uint32_t u = 0; u < per_group; ++u) {
+            const float4 v = accr[(gi8 * per_group + u) * 32u + lane];
+            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+          }
+          gm[gi8 * 32u + lane] = __float_as_uint(mx);  // scores are >= 0: the bit patterns order like the values
+        }
+        __syncwarp();
+        for (uint32_t k2 = 2; k2 <= 256u; k2 <<= 1) {
+          for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (uint32_t i = lane; i < 128u; i += 32) {
+              const uint32_t l = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+              const uint32_t r = l | j;
+              const uint32_t a = gm[l], b = gm[r];
+              const bool desc = (l & k2) == 0;
+              if ((a < b) == desc) { gm[l] = b; gm[r] = a; }
+            }
+            __syncwarp();
+          }
+        }
+        tsc = __uint_as_float(gm[k - 1]);
+        __syncwarp();
+      }
       // one pass reads and tests the block, 4 x 128 bits per lane per step (the next block's first pass overwrites
       // or clears acc[]).  In steady state only a handful of scores survive the threshold; a group with a survivor
       // that finds the buffer full is rewritten with only the scores still to be ranked, for the overflow path.
@@ -1005,6 +1041,7 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   uint32_t nslot = h->bm25_stage_slots >= 0 ? (uint32_t)h->bm25_stage_slots : 8;
   while (nslot > 0 && smem_for(ng, p.R, nslot) > smem_max) --nslot;
   p.nslot = nslot;
+  p.cold_bound = (k <= 256 && nslot >= 2 && !h->bm25_no_cold_bound) ? 1u : 0u;
   p.ng = ng;
   p.r_shift = 0;
   while ((1u << p.r_shift) < p.R) ++p.r_shift;
@@ -1016,7 +1053,7 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   const uint32_t ipw = h->bm25_items_per_warp > 0 ? (uint32_t)h->bm25_items_per_warp : 24;
   uint32_t S = (ipw * groups + nq - 1) / nq;
   if (S < 1) S = 1;
-  if (S > 512) S = 512;  // the per-query merge handles up to 512 sorted lists on its fast path
+  if (S > 256) S = 256;  // the per-query merge is one CTA per query: a few hundred sorted lists at most
   while (S > 1 && (size_t)S * nq * k > b->lists_cap) --S;
   if (S > p.n_blocks) S = p.n_blocks;
   p.J = (p.n_blocks + S - 1) / S;
@@ -1026,9 +1063,10 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  // one CTA per SM; with fewer items than SMs x warps the items still spread over all SMs (each SM's first warps
+  // to reach the counter take them): a single query is latency-bound and every SM brings its own load pipes
   uint32_t grid = (uint32_t)h->num_sms;
-  const uint32_t ctas_useful = (p.S * nq + ng - 1) / ng;
-  if (grid > ctas_useful) grid = ctas_useful;
+  if (grid > p.S * nq) grid = p.S * nq;
   if (ng > 16) bm25_blocked_kernel<768, 0><<<grid, ng * 32, smem, st>>>(p);
   else if (p.R == 2048) bm25_blocked_kernel<512, 2048><<<grid, ng * 32, smem, st>>>(p);
   else bm25_blocked_kernel<512, 0><<<grid, ng * 32, smem, st>>>(p);

@@ -88,6 +88,26 @@ def test_bm25_tuning_options_bit_exact(oi, warps, block_docs, slots):
             assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
 
 
+@pytest.mark.parametrize("k", [1, 7, 100, 128, 256, 300])
+def test_bm25_cold_start_bound_bit_exact(oi, k):
+    """single-query calls start every block without a threshold: the group-maxima bound (k <= 256) and the plain
+    overflow path (bound disabled, or k > 256) must return the same exact lists; few-term vocabularies give many ties"""
+    n, vocab = 50000, 60
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = _weights(corp, n)
+    qs = [[0], [1, 2], [59], [3, 30, 58, 59], [40, 41, 42, 43, 44, 45, 46, 47]]
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=1) as ix:
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.bm25_finalize()
+        for off in (0, 1):
+            ix.set_option("bm25_no_cold_bound", off)
+            for q in qs:
+                ids, sc = ix.search_bm25([q], k)
+                wi, ws = _oracle_lists(corp, w, [q], n, k)
+                assert np.array_equal(ids, wi), (off, q)
+                assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
+
+
 @pytest.mark.parametrize("n,vocab,k,nq", [(30000, 800, 100, 20), (70000, 20000, 10, 5), (9000, 2000, 1000, 2)])
 def test_bm25_sparse_only_path_bit_exact(oi, n, vocab, k, nq):
     """bm25_variant = 100 builds no dense weight columns: every term, however common, walks its postings"""
