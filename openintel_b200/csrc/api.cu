@@ -104,6 +104,10 @@ extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) 
   if ((e = cudaMalloc(&h->d_keys_bm25, B * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
   if ((e = cudaMalloc(&h->d_out_u32, 3 * B * K * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(out)", e);
   if ((e = cudaMalloc(&h->d_out_f32, B * K * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(out)", e);
+  if ((e = cudaHostAlloc(&h->h_pin_in, OI_PIN_BYTES, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  if ((e = cudaHostAlloc(&h->h_pin_out, OI_PIN_BYTES, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  if ((e = cudaMalloc(&h->d_pin_in, OI_PIN_BYTES)) != cudaSuccess) return bail("cudaMalloc(staging)", e);
+  if ((e = cudaMalloc(&h->d_pin_out, OI_PIN_BYTES)) != cudaSuccess) return bail("cudaMalloc(staging)", e);
   *out = h;
   return OI_OK;
 }
@@ -126,6 +130,10 @@ extern "C" void oi_index_destroy(oi_index *h) {
   cudaFree(h->d_out_u32);
   cudaFree(h->d_out_f32);
   cudaFree(h->d_gather);
+  cudaFree(h->d_pin_in);
+  cudaFree(h->d_pin_out);
+  cudaFreeHost(h->h_pin_in);
+  cudaFreeHost(h->h_pin_out);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -293,7 +301,21 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
   if (nq == 0) return OI_OK;
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = h->stream;
-  OI_CK(cudaMemcpyAsync(h->d_queries, queries, (size_t)nq * h->desc.dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  const size_t qbytes = (size_t)nq * h->desc.dim * sizeof(float), n = (size_t)nq * k;
+  if (qbytes <= OI_PIN_BYTES && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
+    memcpy(h->h_pin_in, queries, qbytes);
+    OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, qbytes, cudaMemcpyHostToDevice, st));
+    if ((s = cosine_keys(h, reinterpret_cast<const float *>(h->d_pin_in), nq, k, st))) return s;
+    uint32_t *d_ids = reinterpret_cast<uint32_t *>(h->d_pin_out);
+    float *d_sc = reinterpret_cast<float *>(h->d_pin_out + n * 4);
+    OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, d_ids, d_sc, st, &h->launches));
+    OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 8, cudaMemcpyDeviceToHost, st));
+    OI_CK(cudaStreamSynchronize(st));
+    memcpy(out_ids, h->h_pin_out, n * 4);
+    memcpy(out_scores, h->h_pin_out + n * 4, n * 4);
+    return OI_OK;
+  }
+  OI_CK(cudaMemcpyAsync(h->d_queries, queries, qbytes, cudaMemcpyHostToDevice, st));
   if ((s = cosine_keys(h, h->d_queries, nq, k, st))) return s;
   OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, h->d_out_u32, h->d_out_f32, st, &h->launches));
   OI_CK(cudaMemcpyAsync(out_ids, h->d_out_u32, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -334,8 +356,8 @@ static oi_status bm25_keys(oi_index *h, const uint32_t *d_terms, const uint32_t 
   return OI_OK;
 }
 
-// validates the host-side query term arrays and stages them on the device
-static oi_status stage_terms(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq, cudaStream_t st) {
+// validates the host-side query term arrays
+static oi_status check_terms(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq) {
   if (!oi_bm25_stage_terms(h)) return h->fail(OI_ERR_STATE, "no BM25 index loaded");
   OI_REQUIRE(q_offsets != nullptr, "q_offsets is NULL");
   OI_REQUIRE(q_offsets[0] == 0, "q_offsets[0] must be 0");
@@ -343,11 +365,29 @@ static oi_status stage_terms(oi_index *h, const uint32_t *q_terms, const uint32_
     OI_REQUIRE(q_offsets[j + 1] >= q_offsets[j], "q_offsets not monotone at query %u", j);
     OI_REQUIRE(q_offsets[j + 1] - q_offsets[j] <= 64, "query %u has %u terms (max 64)", j, q_offsets[j + 1] - q_offsets[j]);
   }
+  OI_REQUIRE(q_offsets[nq] == 0 || q_terms != nullptr, "q_terms is NULL");
+  return OI_OK;
+}
+
+// ... and stages them on the device (the large-call path; small calls pack them into the pinned block)
+static oi_status stage_terms(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq, cudaStream_t st) {
+  oi_status s = check_terms(h, q_terms, q_offsets, nq);
+  if (s) return s;
   const uint32_t total = q_offsets[nq];
-  OI_REQUIRE(total == 0 || q_terms != nullptr, "q_terms is NULL");
   if (total) OI_CK(cudaMemcpyAsync(oi_bm25_stage_terms(h), q_terms, (size_t)total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   OI_CK(cudaMemcpyAsync(oi_bm25_stage_offs(h), q_offsets, ((size_t)nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   return OI_OK;
+}
+
+// layout of the pinned input block: [queries f32 nq x dim (may be absent)] [offsets u32 nq + 1] [terms u32 total],
+// every section 16-byte aligned.  Returns the total size, 0 if it does not fit.
+static size_t pin_in_layout(size_t qbytes, uint32_t nq, uint32_t total_terms, size_t *off_offs, size_t *off_terms) {
+  const size_t a = (qbytes + 15) & ~(size_t)15;
+  const size_t b = a + ((((size_t)nq + 1) * 4 + 15) & ~(size_t)15);
+  const size_t c = b + (((size_t)total_terms * 4 + 15) & ~(size_t)15);
+  *off_offs = a;
+  *off_terms = b;
+  return c <= OI_PIN_BYTES ? (c ? c : 16) : 0;
 }
 
 extern "C" oi_status oi_search_bm25_dev(oi_index *h, const uint32_t *d_q_terms, const uint32_t *d_q_offsets, uint32_t nq,
@@ -374,6 +414,22 @@ extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const 
   OI_REQUIRE(out_ids && out_scores, "NULL host pointer");
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = h->stream;
+  if ((s = check_terms(h, q_terms, q_offsets, nq))) return s;
+  const size_t n = (size_t)nq * k;
+  size_t o_offs, o_terms;
+  const size_t in_bytes = pin_in_layout(0, nq, q_offsets[nq], &o_offs, &o_terms);
+  if (in_bytes && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
+    memcpy(h->h_pin_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
+    if (q_offsets[nq]) memcpy(h->h_pin_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);
+    OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, in_bytes, cudaMemcpyHostToDevice, st));
+    if ((s = bm25_keys(h, reinterpret_cast<const uint32_t *>(h->d_pin_in + o_terms), reinterpret_cast<const uint32_t *>(h->d_pin_in + o_offs), nq, k, st))) return s;
+    OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, reinterpret_cast<uint32_t *>(h->d_pin_out), reinterpret_cast<float *>(h->d_pin_out + n * 4), st, &h->launches));
+    OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 8, cudaMemcpyDeviceToHost, st));
+    OI_CK(cudaStreamSynchronize(st));
+    memcpy(out_ids, h->h_pin_out, n * 4);
+    memcpy(out_scores, h->h_pin_out + n * 4, n * 4);
+    return OI_OK;
+  }
   if ((s = stage_terms(h, q_terms, q_offsets, nq, st))) return s;
   if ((s = bm25_keys(h, oi_bm25_stage_terms(h), oi_bm25_stage_offs(h), nq, k, st))) return s;
   OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, h->d_out_u32, h->d_out_f32, st, &h->launches));
@@ -422,7 +478,29 @@ extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const u
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = h->stream;
   const size_t n = (size_t)nq * k, BK = (size_t)h->desc.max_batch * h->desc.max_k;
-  OI_CK(cudaMemcpyAsync(h->d_queries, queries, (size_t)nq * h->desc.dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  const size_t qbytes = (size_t)nq * h->desc.dim * sizeof(float);
+  if ((s = check_terms(h, q_terms, q_offsets, nq))) return s;
+  size_t o_offs, o_terms;
+  const size_t in_bytes = pin_in_layout(qbytes, nq, q_offsets[nq], &o_offs, &o_terms);
+  if (in_bytes && n * 16 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
+    memcpy(h->h_pin_in, queries, qbytes);
+    memcpy(h->h_pin_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
+    if (q_offsets[nq]) memcpy(h->h_pin_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);
+    OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, in_bytes, cudaMemcpyHostToDevice, st));
+    uint32_t *d_ids = reinterpret_cast<uint32_t *>(h->d_pin_out), *d_rc = d_ids + 2 * n, *d_rb = d_ids + 3 * n;
+    float *d_rrf = reinterpret_cast<float *>(d_ids + n);
+    if ((s = hybrid_enqueue(h, reinterpret_cast<const float *>(h->d_pin_in), reinterpret_cast<const uint32_t *>(h->d_pin_in + o_terms),
+                            reinterpret_cast<const uint32_t *>(h->d_pin_in + o_offs), nq, k, rrf_k, d_ids, d_rrf, d_rc, d_rb, st)))
+      return s;
+    OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 16, cudaMemcpyDeviceToHost, st));
+    OI_CK(cudaStreamSynchronize(st));
+    memcpy(out_ids, h->h_pin_out, n * 4);
+    memcpy(out_rrf, h->h_pin_out + n * 4, n * 4);
+    memcpy(out_rank_cos, h->h_pin_out + n * 8, n * 4);
+    memcpy(out_rank_bm25, h->h_pin_out + n * 12, n * 4);
+    return OI_OK;
+  }
+  OI_CK(cudaMemcpyAsync(h->d_queries, queries, qbytes, cudaMemcpyHostToDevice, st));
   if ((s = stage_terms(h, q_terms, q_offsets, nq, st))) return s;
   uint32_t *d_ids = h->d_out_u32, *d_rc = h->d_out_u32 + BK, *d_rb = h->d_out_u32 + 2 * BK;
   if ((s = hybrid_enqueue(h, h->d_queries, oi_bm25_stage_terms(h), oi_bm25_stage_offs(h), nq, k, rrf_k, d_ids, h->d_out_f32, d_rc, d_rb, st))) return s;

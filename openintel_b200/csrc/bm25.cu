@@ -51,6 +51,7 @@ struct OiBm25 {
   int *d_dense_slot = nullptr;    // [n_terms] column index or -1
   uint32_t n_dense = 0, dense_stride = 0;
   bool finalized = false;
+  bool attr_set = false;          // dynamic shared-memory limit of the scoring kernels raised
   // search workspace
   uint32_t *d_qterms = nullptr;   // [max_batch][64] sorted distinct valid terms
   uint32_t *d_qnt = nullptr;      // [max_batch]
@@ -229,7 +230,7 @@ __device__ __forceinline__ void term_setup(TermRegs &T, const Bm25Params &p, uin
     T.den = (uint32_t)slot;
     T.nxt = doc0;
   } else {          // one binary search positions the cursor at the super-range start
-    u64 a = lo, b = hi;
+    u64 a = lo, b = doc0 ? hi : lo;  // nothing precedes the shard's first document
     while (a < b) {
       const u64 mid = a + ((b - a) >> 1);
       if (__ldg(p.doc_ids + mid) < doc0) a = mid + 1; else b = mid;
@@ -538,31 +539,53 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
   }
 }
 
-// sorts each query's terms ascending, drops duplicates, unknown terms and empty lists
-__global__ void bm25_prep_queries_kernel(const uint32_t *q_terms, const uint32_t *q_offs, uint32_t nq,
-                                         const u64 *term_off, uint32_t n_terms, uint32_t *out_terms,
-                                         uint32_t *out_nt, u64 *gthr, uint32_t *counter) {
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q == 0) *counter = 0;
-  if (q >= nq) return;
-  gthr[q] = 0ull;
-  uint32_t *o = out_terms + (size_t)q * OI_BM25_MAX_QTERMS;
+// sorts each query's terms ascending, drops duplicates, unknown terms and empty lists.  One warp per query: lane l
+// looks at input terms l and 32 + l (all list-length loads in flight at once), then every valid first occurrence
+// ranks itself among the others with shuffles -- a single query used to spend 8 us here on serial dependent loads.
+__global__ void __launch_bounds__(128) bm25_prep_queries_kernel(const uint32_t *q_terms, const uint32_t *q_offs, uint32_t nq,
+                                                               const u64 *term_off, uint32_t n_terms, uint32_t *out_terms,
+                                                               uint32_t *out_nt, u64 *gthr, uint32_t *counter) {
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+  if (q >= nq) return;  // warp-uniform
+  if (lane == 0) gthr[q] = 0ull;
   const uint32_t lo = q_offs[q];
   uint32_t n_in = q_offs[q + 1] - lo;
   if (n_in > OI_BM25_MAX_QTERMS) n_in = OI_BM25_MAX_QTERMS;
-  uint32_t n = 0;
-  for (uint32_t i = 0; i < n_in; ++i) {
-    const uint32_t t = q_terms[lo + i];
-    if (t >= n_terms || term_off[t + 1] == term_off[t]) continue;
-    // insertion into the sorted distinct prefix
-    uint32_t at = 0;
-    while (at < n && o[at] < t) ++at;
-    if (at < n && o[at] == t) continue;
-    for (uint32_t j = n; j > at; --j) o[j] = o[j - 1];
-    o[at] = t;
-    ++n;
+  uint32_t t[2];
+  bool ok[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const uint32_t i = (uint32_t)lane + 32u * hh;
+    t[hh] = i < n_in ? q_terms[lo + i] : 0xFFFFFFFFu;
+    ok[hh] = i < n_in && t[hh] < n_terms;
+    if (ok[hh]) ok[hh] = term_off[t[hh] + 1] != term_off[t[hh]];
   }
-  out_nt[q] = n;
+  // first occurrence of its value among the valid inputs (input order)
+  bool first[2] = {ok[0], ok[1]};
+  for (uint32_t j = 0; j < n_in; ++j) {
+    const uint32_t tj = __shfl_sync(0xFFFFFFFFu, j < 32 ? t[0] : t[1], (int)(j & 31));
+    const bool okj = __shfl_sync(0xFFFFFFFFu, (int)(j < 32 ? ok[0] : ok[1]), (int)(j & 31)) != 0;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+      if (okj && tj == t[hh] && j < (uint32_t)lane + 32u * hh) first[hh] = false;
+  }
+  // rank = number of kept terms below mine
+  uint32_t rank[2] = {0, 0};
+  for (uint32_t j = 0; j < n_in; ++j) {
+    const uint32_t tj = __shfl_sync(0xFFFFFFFFu, j < 32 ? t[0] : t[1], (int)(j & 31));
+    const bool kj = __shfl_sync(0xFFFFFFFFu, (int)(j < 32 ? first[0] : first[1]), (int)(j & 31)) != 0;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+      if (kj && tj < t[hh]) ++rank[hh];
+  }
+  uint32_t *o = out_terms + (size_t)q * OI_BM25_MAX_QTERMS;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh)
+    if (first[hh]) o[rank[hh]] = t[hh];
+  const uint32_t n = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, first[0])) + (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, first[1]));
+  if (lane == 0) out_nt[q] = n;
 }
 
 // per-posting folded weight, SPEC §3 association, one IEEE op per line (file built with -fmad=false)
@@ -1003,7 +1026,7 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   OiBm25 *b = h->bm25;
   if (!b || !b->finalized) return h->fail(OI_ERR_STATE, "BM25 index not loaded / not finalized");
   if (nq == 0) return OI_OK;
-  bm25_prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_q_terms, d_q_offs, nq, b->d_term_off, b->n_terms,
+  bm25_prep_queries_kernel<<<(nq + 3) / 4, 128, 0, st>>>(d_q_terms, d_q_offs, nq, b->d_term_off, b->n_terms,
                                                              b->d_qterms, b->d_qnt, b->d_gthr, b->d_counter);
   ++h->launches;
   BM_CK(cudaGetLastError());
@@ -1060,9 +1083,12 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   p.S = (p.n_blocks + p.J - 1) / p.J;
   if ((size_t)p.S * nq * k > b->lists_cap) return h->fail(OI_ERR_CUDA, "internal: BM25 list workspace too small (%u x %u)", p.S, nq);
   const size_t smem = smem_for(ng, p.R, nslot);
-  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (!b->attr_set) {  // once per index (the attribute is per function and device)
+    BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    b->attr_set = true;
+  }
   // one CTA per SM; with fewer items than SMs x warps the items still spread over all SMs (each SM's first warps
   // to reach the counter take them): a single query is latency-bound and every SM brings its own load pipes
   uint32_t grid = (uint32_t)h->num_sms;

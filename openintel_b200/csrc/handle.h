@@ -6,6 +6,8 @@ struct OiBm25;  // bm25.cu
 struct OiComm;  // comm.cu
 struct OiGemm;  // cosine_gemm.cu
 
+#define OI_PIN_BYTES (1u << 20)
+
 struct oi_index {
   oi_index_desc desc{};
   int num_sms = 0;
@@ -29,6 +31,10 @@ struct oi_index {
   u64 *d_gather = nullptr;        // [world][max_batch][max_k]
   uint32_t *d_out_u32 = nullptr;  // 3 x [max_batch][max_k]
   float *d_out_f32 = nullptr;     // [max_batch][max_k]
+  // small host-buffer calls go through one pinned staging block each way: one H2D copy of (queries | terms |
+  // offsets) and one D2H copy of (ids | scores | ranks) instead of 3 + 4 copies from / to pageable memory
+  unsigned char *h_pin_in = nullptr, *h_pin_out = nullptr;  // OI_PIN_BYTES each (cudaHostAlloc)
+  unsigned char *d_pin_in = nullptr, *d_pin_out = nullptr;  // device mirrors
 
   // batched cosine on the tensor cores (cosine_gemm.cu); workspace is created on first use
   OiGemm *gemm = nullptr;
