@@ -283,10 +283,11 @@ __device__ __forceinline__ void dense_sweep(const float4 *__restrict__ c0, const
 // all lists in flight at once, completion counted on the warp's mbarrier -- then the present lists are visited
 // in order: dense terms add their columns (two consecutive ones share a sweep), a sparse term consumes its staged
 // chunk (and, for a segment longer than the chunk, goes on with direct loads).  `fresh` = acc[] holds nothing for
-// this block yet: a dense first pass overwrites it, a sparse first pass clears it first.
+// this block yet: a dense first pass overwrites it, a sparse first pass clears it first.  `touched` accumulates an
+// upper bound of the documents with a positive score (postings applied; R per dense sweep).
 template <uint32_t RT>
 __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, float *acc, uint4 *stage, void *mbar, uint32_t &phase,
-                                             bool &fresh, uint32_t bbase, uint32_t bend, int lane) {
+                                             bool &fresh, uint32_t &touched, uint32_t bbase, uint32_t bend, int lane) {
   const uint32_t R = RT ? RT : p.R;
   const bool present = T.nxt < bend;
   const uint32_t pm = __ballot_sync(0xFFFFFFFFu, present);
@@ -329,6 +330,7 @@ __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, f
         else dense_sweep<false, 1>(c0, c0, a4, R, lane);
       }
       fresh = false;
+      touched += R;
       if (lane == i || lane == i2) T.nxt = nxt_dense;
     } else {
       if (fresh) {  // a sparse first pass scatters into the block: clear it first
@@ -349,6 +351,7 @@ __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, f
       }
       uint32_t pos_new, nxt;
       sparse_pass(p.post, base, cur, end, bbase, bend, acc, lane, sp, &pos_new, &nxt);
+      touched += pos_new - cur;
       if (lane == i) { T.cur = pos_new; T.nxt = nxt; }
     }
     __syncwarp();  // the next pass may touch the same documents
@@ -421,16 +424,17 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
       // the grid-wide threshold is requested now and consumed after the passes
       const u64 gthr_now = ld_relaxed_u64(p.gthr + q);
       bool fresh = true;  // acc[] holds the previous block's scores until the first pass overwrites or clears it
-      block_passes<RT>(T0, p, acc, stage, mbar, phase, fresh, bbase, bend, lane);
-      if (nt > 32) block_passes<RT>(T1, p, acc, stage, mbar, phase, fresh, bbase, bend, lane);
+      uint32_t touched = 0;
+      block_passes<RT>(T0, p, acc, stage, mbar, phase, fresh, touched, bbase, bend, lane);
+      if (nt > 32) block_passes<RT>(T1, p, acc, stage, mbar, phase, fresh, touched, bbase, bend, lane);
       // ---- selection: positive scores that beat the running threshold -------------------------
       const u64 thr = max(ctl->thr, gthr_now);
       float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
       __syncwarp();
-      if (thr == 0ull && p.cold_bound) {
+      if (thr == 0ull && p.cold_bound && touched + ctl->cnt > cap) {
         // cold start (no threshold yet: the first block of an item whose query has none either, i.e. every block of a
-        // single-query call): without a bound every positive score is a candidate and the buffer is sorted a dozen
-        // times.  The k-th largest of the block's 256 group maxima (groups of R / 256 documents) is a score at
+        // single-query call) and more positive scores than the buffer can take: without a bound every one of them
+        // is a candidate and the buffer is sorted a dozen times.  The k-th largest of the block's 256 group maxima (groups of R / 256 documents) is a score at
         // least k documents of the block reach, so nothing below it can be in the top k: one sort of 256 values
         // replaces the repeated compactions.  The staging buffer is idle here and serves as scratch.
         uint32_t *gm = reinterpret_cast<uint32_t *>(stage);
