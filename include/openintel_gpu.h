@@ -147,7 +147,11 @@ oi_status oi_lexicon_analyze(int32_t device, const uint8_t *texts, const uint64_
 uint64_t oi_index_launch_count(const oi_index *h);
 /* named integer knobs: "cosine_variant" (0 = ldg, 1 = bulk-copy pipeline), "cosine_gemm_min_batch"
  * (bf16 batches of at least this many queries take the tcgen05 tensor-core path; 0 = never),
- * "cosine_gemm_cap" / "cosine_gemm_sample_tiles" (tests: force list compaction / the two-pass flow) */
+ * "cosine_gemm_cap" / "cosine_gemm_sample_tiles" (tests: force list compaction / the two-pass flow);
+ * BM25 schedule: "bm25_warps" (warps per CTA), "bm25_block_docs" (documents per block, power of two >= 1024),
+ * "bm25_stage_slots" (TMA-staged 64-posting chunks per warp), "bm25_items_per_warp", "bm25_dense_div" (before
+ * finalize: a term in >= n_docs / div documents gets a dense weight column), "bm25_no_cold_bound" (tests);
+ * every setting returns the same lists bit for bit.  "comm_debug_skip_gather": timing experiments only. */
 oi_status oi_index_set_option(oi_index *h, const char *name, int64_t value);
 /* tests: the raw nq x n_docs f32 score matrix of the tensor-core path (bf16 index, small shards) */
 oi_status oi_debug_cosine_gemm_scores(oi_index *h, const float *queries, uint32_t nq, float *out_scores);
