@@ -1043,8 +1043,8 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   uint32_t cap = 256;
   while (cap < 2 * k) cap <<= 1;
   p.cap = cap;
-  // one warp per work item.  k <= 128: 16 warps per CTA with 2048-document blocks and 8 staged chunks per warp
-  // (224 KB of shared memory); larger k: 8 / 4 / 2 warps with 4096 / 8192 / 16384-document blocks, as many as 64 KB
+  // one warp per work item.  k <= 128: 20 warps per CTA with 2048-document blocks and 2 staged chunks per warp
+  // (220 KB of shared memory; 16 warps with 8 chunks each measure 6 % slower); larger k: 8 / 4 / 2 warps with 4096 / 8192 / 16384-document blocks, as many as 64 KB
   // of candidate buffers allow.
   // Tuning options (oi_index_set_option): bm25_warps, bm25_block_docs, bm25_stage_slots; bm25_variant 1..15 keeps
   // its old meaning (warps per CTA rounded down to a power of two, 32768 / warps documents per block).
@@ -1056,6 +1056,7 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   uint32_t ng = 16;
   while (ng > 1 && ng * cap > 8192) ng >>= 1;
   p.R = OI_BM25_ACC_FLOATS / ng;
+  if (cap <= 256) ng = 20;  // 2048-document blocks: 20 x (8 KB scores + 2 KB candidates + 1 KB staging) = 220 KB
   if (h->bm25_variant >= 1 && h->bm25_variant <= 15) {
     uint32_t f = 1;
     while (f * 2 <= (uint32_t)h->bm25_variant) f <<= 1;
@@ -1091,13 +1092,17 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
     BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<768, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<576, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BM_CK(cudaFuncSetAttribute(bm25_blocked_kernel<640, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     b->attr_set = true;
   }
   // one CTA per SM; with fewer items than SMs x warps the items still spread over all SMs (each SM's first warps
   // to reach the counter take them): a single query is latency-bound and every SM brings its own load pipes
   uint32_t grid = (uint32_t)h->num_sms;
   if (grid > p.S * nq) grid = p.S * nq;
-  if (ng > 16) bm25_blocked_kernel<768, 0><<<grid, ng * 32, smem, st>>>(p);
+  if (ng > 16 && ng <= 18 && p.R == 2048) bm25_blocked_kernel<576, 2048><<<grid, ng * 32, smem, st>>>(p);
+  else if (ng > 18 && ng <= 20 && p.R == 2048) bm25_blocked_kernel<640, 2048><<<grid, ng * 32, smem, st>>>(p);
+  else if (ng > 16) bm25_blocked_kernel<768, 0><<<grid, ng * 32, smem, st>>>(p);
   else if (p.R == 2048) bm25_blocked_kernel<512, 2048><<<grid, ng * 32, smem, st>>>(p);
   else bm25_blocked_kernel<512, 0><<<grid, ng * 32, smem, st>>>(p);
   ++h->launches;
