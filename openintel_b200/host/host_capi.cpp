@@ -1,6 +1,7 @@
 // host_capi.cpp — extern "C" shim over the header-only host layer so that the CPU test-suite can
 // drive the tokenizer and the index builder (libopenintel_host.so; no CUDA in here).
 #include "openintel_host.hpp"
+#include "openintel_store.hpp"
 
 using openintel::IndexBuilder;
 
@@ -56,6 +57,53 @@ uint64_t oih_tokenize(const uint8_t *text, uint64_t len, uint8_t *out, uint64_t 
   });
   std::memcpy(out, joined.data(), std::min<uint64_t>(cap, joined.size()));
   return joined.size();
+}
+
+// ---- SQLite post store (openintel_store.hpp); errors come back as -1 + oih_last_error() ---------
+static thread_local std::string g_err;
+const char *oih_last_error() { return g_err.c_str(); }
+void *oih_store_open(const char *path) {
+  try {
+    return new openintel::SqlitePostStore(path);
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void oih_store_close(void *s) { delete static_cast<openintel::SqlitePostStore *>(s); }
+void oih_store_info(void *s, uint64_t *n_posts, uint32_t *dim) {
+  const auto *st = static_cast<openintel::SqlitePostStore *>(s);
+  *n_posts = st->n_posts();
+  *dim = st->dim();
+}
+// adds every post of the store to the builder, doc_id order; returns the number of posts or -1
+int64_t oih_store_lift_posts(void *s, void *b) {
+  try {
+    IndexBuilder *ix = static_cast<IndexBuilder *>(b);
+    int64_t n = 0;
+    static_cast<openintel::SqlitePostStore *>(s)->for_each_post([&](const openintel::SocialPost &p) { ix->add(p); ++n; });
+    return n;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// out: [n_posts][dim] f32, rows L2-normalised; returns 0 or -1
+int oih_store_embeddings(void *s, float *out) {
+  try {
+    const std::vector<float> rows = static_cast<openintel::SqlitePostStore *>(s)->embeddings();
+    std::memcpy(out, rows.data(), rows.size() * sizeof(float));
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// post id of document `doc` as added through oih_store_lift_posts; returns its length
+uint32_t oih_builder_post_id(void *b, uint32_t doc, uint8_t *out, uint32_t cap) {
+  const std::string &s = static_cast<IndexBuilder *>(b)->post_ids().at(doc);
+  std::memcpy(out, s.data(), std::min<size_t>(cap, s.size()));
+  return (uint32_t)s.size();
 }
 
 }  // extern "C"

@@ -2,11 +2,14 @@
 //   host_demo <posts.txt> <embeddings.f32> <dim> <queries.txt> <query_embeddings.f32> <k>
 // posts.txt / queries.txt: one text per line.  Prints one line per hit: "q rank doc_id rrf rc rb",
 // then one line per post "signal i polarity speculative" from the GPU PostAnalyzer.
+//   host_demo --store <posts.db> <queries.txt> <query_embeddings.f32> <k>
+// lifts the index out of a SQLite post store (openintel_store.hpp) and prints "hit q rank doc_id rrf rc rb post_id".
 #include <cstdio>
 #include <fstream>
 #include <iostream>
 
 #include "openintel_host.hpp"
+#include "openintel_store.hpp"
 
 using namespace openintel;
 
@@ -25,7 +28,50 @@ static std::vector<float> read_f32(const char *path) {
   return v;
 }
 
+static int store_mode(int argc, char **argv) {
+  if (argc != 6) { std::fprintf(stderr, "usage: host_demo --store posts.db queries.txt qemb.f32 k\n"); return 2; }
+  const SqlitePostStore store(argv[2]);
+  const std::vector<std::string> qtexts = read_lines(argv[3]);
+  std::vector<float> qemb = read_f32(argv[4]);
+  const size_t k = std::stoul(argv[5]);
+  const uint32_t dim = store.dim();
+  if (qemb.size() != qtexts.size() * dim) throw std::runtime_error("query embedding file size mismatch");
+  IndexBuilder ix;
+  const auto search = lift_index(store, ix, 0, (uint32_t)k, (uint32_t)std::max<size_t>(qtexts.size(), 1));
+  std::vector<SearchQuery> queries;
+  for (size_t j = 0; j < qtexts.size(); ++j) {
+    SearchQuery q;
+    q.embedding.assign(qemb.begin() + j * dim, qemb.begin() + (j + 1) * dim);
+    float ss = 0.0f;  // queries are normalised by the caller (SPEC §2)
+    for (float v : q.embedding) ss += v * v;
+    const float nrm = std::sqrt(ss);
+    if (nrm > 0.0f)
+      for (float &v : q.embedding) v /= nrm;
+    q.terms = ix.query_terms(qtexts[j]);
+    queries.push_back(std::move(q));
+  }
+  const HybridSearch &port = *search;
+  const auto hits = port.search(queries, k);
+  for (size_t j = 0; j < hits.size(); ++j)
+    for (size_t i = 0; i < hits[j].size(); ++i)
+      std::printf("hit %zu %zu %u %.9g %u %u %s\n", j, i, hits[j][i].doc_id, hits[j][i].rrf, hits[j][i].rank_cosine, hits[j][i].rank_bm25,
+                  ix.post_ids()[hits[j][i].doc_id].c_str());
+  std::printf("store %llu posts dim %u terms %u\n", (unsigned long long)store.n_posts(), dim, ix.n_terms());
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 2 && std::string(argv[1]) == "--store") {
+    try {
+      return store_mode(argc, argv);
+    } catch (const DomainError &e) {
+      std::fprintf(stderr, "DomainError(%d): %s\n", (int)e.kind, e.what());
+      return 1;
+    } catch (const std::exception &e) {
+      std::fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
   if (argc != 7) { std::fprintf(stderr, "usage: host_demo posts.txt emb.f32 dim queries.txt qemb.f32 k\n"); return 2; }
   try {
     const std::vector<std::string> texts = read_lines(argv[1]);

@@ -34,6 +34,17 @@ def load():
         L.oih_builder_term.restype = u32
         L.oih_builder_term.argtypes = [vp, u32, C.c_char_p, u32]
         L.oih_tokenize.restype = u64
+        L.oih_last_error.restype = C.c_char_p
+        L.oih_store_open.restype = vp
+        L.oih_store_open.argtypes = [C.c_char_p]
+        L.oih_store_close.argtypes = [vp]
+        L.oih_store_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u32)]
+        L.oih_store_lift_posts.restype = C.c_int64
+        L.oih_store_lift_posts.argtypes = [vp, vp]
+        L.oih_store_embeddings.restype = C.c_int
+        L.oih_store_embeddings.argtypes = [vp, vp]
+        L.oih_builder_post_id.restype = u32
+        L.oih_builder_post_id.argtypes = [vp, u32, C.c_char_p, u32]
         L.oih_tokenize.argtypes = [C.c_char_p, u64, C.c_char_p, u64]
         _lib = L
     return _lib
@@ -88,8 +99,47 @@ class IndexBuilder:
         self.L.oih_builder_term(self.b, term_id, buf, n)
         return buf.raw[:n].decode("ascii")
 
+    def post_id(self, doc):
+        n = self.L.oih_builder_post_id(self.b, doc, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.oih_builder_post_id(self.b, doc, buf, n)
+        return buf.raw[:n].decode("utf-8")
+
     def query_terms(self, text):
         raw = text.encode("utf-8")
         out = np.empty(max(len(raw), 1), dtype=np.uint32)
         n = self.L.oih_builder_query_terms(self.b, raw, len(raw), out.ctypes.data, len(out))
         return out[:n].copy()
+
+
+class CppPostStore:
+    """The C++ reader of the SQLite post store (host/openintel_store.hpp), for tests: the compiled host layer must
+    lift the same CSR and the same normalised rows out of a store as openintel_b200.store does."""
+
+    def __init__(self, path):
+        self.L = load()
+        self.s = self.L.oih_store_open(path.encode("utf-8"))
+        if not self.s:
+            raise OSError(self.L.oih_last_error().decode("utf-8", "replace"))
+        n, d = C.c_uint64(), C.c_uint32()
+        self.L.oih_store_info(self.s, C.byref(n), C.byref(d))
+        self.n_posts, self.dim = n.value, d.value
+
+    def close(self):
+        if getattr(self, "s", None):
+            self.L.oih_store_close(self.s)
+            self.s = None
+
+    __del__ = close
+
+    def lift_posts(self, builder):
+        n = self.L.oih_store_lift_posts(self.s, builder.b)
+        if n < 0:
+            raise ValueError(self.L.oih_last_error().decode("utf-8", "replace"))
+        return n
+
+    def embeddings(self):
+        out = np.empty((self.n_posts, self.dim), dtype=np.float32)
+        if self.L.oih_store_embeddings(self.s, out.ctypes.data) != 0:
+            raise ValueError(self.L.oih_last_error().decode("utf-8", "replace"))
+        return out

@@ -87,3 +87,44 @@ def test_store_hybrid_matches_oracle(oi, tmp_path, n, vocab, dim, k):
         if j == 2:
             assert all(h["rank_bm25"] == 0 for h in hits)  # no known term: the fused list is the cosine list
     conn.close()
+
+
+def test_cpp_host_layer_lifts_the_store_and_searches(oi, tmp_path):
+    """host_demo --store: SqlitePostStore -> IndexBuilder -> GpuHybridSearch in C++ returns the lists the Python
+    lift returns on the same store file (BM25 / RRF bit-exact; the cosine list may differ inside the f32 tie band
+    because the two lifts sum the row norms in a different order)"""
+    import subprocess
+    from openintel_b200 import hostlib, store
+    n, vocab, dim, k = 4000, 3000, 96, 10
+    posts, _ = store.synth_posts(n, vocab, O.SEED, O)
+    emb = O.synth_rows_f32(n, dim) * np.float32(2.0)
+    path = str(tmp_path / "posts.db")
+    conn = store.open_store(path, dim=dim)
+    store.insert_posts(conn, posts, emb)
+    texts = [" ".join(posts[11]["text"].split()[:6]), " ".join(posts[n - 5]["text"].split()[:4]) + " zzzunknown"]
+    qv = O.synth_rows_f32(len(texts), dim, stream=1)
+    with store.StoreIndex(conn, max_k=k, max_batch=4) as sx:
+        want = sx.search(texts, qv, k)
+    conn.close()
+    (tmp_path / "queries.txt").write_text("\n".join(texts) + "\n")
+    qv.tofile(tmp_path / "qemb.f32")
+    demo = os.path.join(os.path.dirname(hostlib.__file__), "host", "host_demo")
+    r = subprocess.run([demo, "--store", path, str(tmp_path / "queries.txt"), str(tmp_path / "qemb.f32"), str(k)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = {}
+    for line in r.stdout.splitlines():
+        f = line.split()
+        if f[0] == "hit":
+            got.setdefault(int(f[1]), []).append(dict(doc_id=int(f[3]), rrf=float(np.float32(f[4])), rank_cosine=int(f[5]), rank_bm25=int(f[6]), id=f[7]))
+    assert "store %d posts dim %d" % (n, dim) in r.stdout
+    for j in range(len(texts)):
+        if [h["doc_id"] for h in got[j]] == [h["doc_id"] for h in want[j]]:
+            assert got[j] == want[j]
+        else:
+            assert sorted(h["doc_id"] for h in got[j]) == sorted(h["doc_id"] for h in want[j])
+        assert all(h["id"] == "post-%d" % h["doc_id"] for h in got[j])
+    # a missing store is a DomainError::SourceFailure, not a crash
+    r = subprocess.run([demo, "--store", str(tmp_path / "nope.db"), str(tmp_path / "queries.txt"), str(tmp_path / "qemb.f32"), str(k)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "post-store" in r.stderr

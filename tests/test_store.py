@@ -102,3 +102,31 @@ def test_store_rejects_bad_rows(tmp_path):
     store.open_store(path, dim=4).close()
     with pytest.raises(ValueError):  # the store's dimension is fixed at creation
         store.open_store(path, dim=5)
+
+
+def test_cpp_store_reader_lifts_the_same_index(tmp_path):
+    """host/openintel_store.hpp (C++, libsqlite3 bound with dlopen) vs openintel_b200.store (Python) on one store file"""
+    path = str(tmp_path / "posts.db")
+    posts = _posts(500)
+    posts[7] = dict(posts[7], text="Ünïcode café — $AAPL 0dte \U0001F680 calls", id="post-unicode")
+    emb = np.random.RandomState(9).randn(500, 40).astype(np.float32) * 7
+    emb[3] = 0.0
+    conn = store.open_store(path, dim=40)
+    store.insert_posts(conn, posts, emb)
+    b_py, csr_py, ids_py = store.lift_csr(conn)
+    rows_py = store.lift_embeddings(conn, 500, 40)
+    conn.close()
+    cs = hostlib.CppPostStore(path)
+    assert (cs.n_posts, cs.dim) == (500, 40)
+    b = hostlib.IndexBuilder()
+    assert cs.lift_posts(b) == 500
+    csr = b.finish()
+    for name in ("term_offsets", "doc_ids", "tfs", "doc_len"):
+        assert np.array_equal(csr[name], csr_py[name]), name
+    assert [b.term(i) for i in range(csr["n_terms"])] == [b_py.term(i) for i in range(csr_py["n_terms"])]
+    assert [b.post_id(d) for d in (0, 7, 499)] == [ids_py[0], "post-unicode", ids_py[499]]
+    rows = cs.embeddings()
+    assert np.all(rows[3] == 0) and np.allclose(rows, rows_py, atol=2e-7)  # f32 norms summed in a different order
+    cs.close()
+    with pytest.raises(OSError):
+        hostlib.CppPostStore(str(tmp_path / "missing.db"))
