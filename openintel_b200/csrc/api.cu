@@ -261,10 +261,11 @@ static oi_status check_search_args(oi_index *h, uint32_t nq, uint32_t k) {
 }
 
 // local scan -> (multi-GPU: all-gather + merge) -> global cosine key lists in d_keys_cos
-static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, cudaStream_t st) {
+// `local_only` (multi-GPU hybrid): leave the shard-local lists there and skip the exchange
+static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, cudaStream_t st, u64 *local_only = nullptr) {
   if (h->emb_rows_loaded < h->desc.n_docs) return h->fail(OI_ERR_STATE, "embeddings not loaded (%llu of %llu rows)", (unsigned long long)h->emb_rows_loaded, (unsigned long long)h->desc.n_docs);
   if (nq == 0) return OI_OK;
-  u64 *local = h->world > 1 ? h->d_keys_local : h->d_keys_cos;
+  u64 *local = local_only ? local_only : (h->world > 1 ? h->d_keys_local : h->d_keys_cos);
   if (h->gemm_min_batch > 0 && nq >= (uint32_t)h->gemm_min_batch && oi_gemm_eligible(h, nq, k)) {
     // batched bf16 queries: one pass of the matrix through the tensor cores serves the whole batch
     oi_status s = oi_gemm_local_keys(h, d_queries, nq, k, local, nullptr, st);
@@ -273,7 +274,7 @@ static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, u
     OI_CK(oi_launch_cosine_scan(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, (uint32_t)h->desc.doc_base, d_queries, nq, k,
                                 h->cws, local, h->cosine_variant, h->num_sms, st, &h->launches));
   }
-  if (h->world > 1) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_cos, st);
+  if (h->world > 1 && !local_only) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_cos, st);
   return OI_OK;
 }
 
@@ -347,12 +348,13 @@ extern "C" oi_status oi_debug_cosine_gemm_scores(oi_index *h, const float *queri
 }
 
 // local BM25 lists -> (multi-GPU: all-gather + merge) -> global BM25 key lists in d_keys_bm25
-static oi_status bm25_keys(oi_index *h, const uint32_t *d_terms, const uint32_t *d_offs, uint32_t nq, uint32_t k, cudaStream_t st) {
+static oi_status bm25_keys(oi_index *h, const uint32_t *d_terms, const uint32_t *d_offs, uint32_t nq, uint32_t k, cudaStream_t st,
+                           u64 *local_only = nullptr) {
   if (nq == 0) return OI_OK;
-  u64 *local = h->world > 1 ? h->d_keys_local : h->d_keys_bm25;
+  u64 *local = local_only ? local_only : (h->world > 1 ? h->d_keys_local : h->d_keys_bm25);
   oi_status s = oi_bm25_local_keys(h, d_terms, d_offs, nq, k, local, st);
   if (s) return s;
-  if (h->world > 1) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_bm25, st);
+  if (h->world > 1 && !local_only) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_bm25, st);
   return OI_OK;
 }
 
@@ -444,8 +446,16 @@ static oi_status hybrid_enqueue(oi_index *h, const float *d_queries, const uint3
                                 uint32_t nq, uint32_t k, uint32_t rrf_k, uint32_t *d_ids, float *d_rrf, uint32_t *d_rc,
                                 uint32_t *d_rb, cudaStream_t st) {
   oi_status s;
-  if ((s = cosine_keys(h, d_queries, nq, k, st))) return s;
-  if ((s = bm25_keys(h, d_terms, d_offs, nq, k, st))) return s;
+  if (h->world > 1) {
+    // sharded: both local lists first, then ONE exchange for the two modalities (SPEC §5: RRF on the global ranks)
+    u64 *loc_cos = h->d_keys_local, *loc_bm = h->d_keys_local + (size_t)nq * k;
+    if ((s = cosine_keys(h, d_queries, nq, k, st, loc_cos))) return s;
+    if ((s = bm25_keys(h, d_terms, d_offs, nq, k, st, loc_bm))) return s;
+    if ((s = oi_comm_gather_merge2(h, h->d_keys_local, nq, k, h->d_keys_cos, h->d_keys_bm25, st))) return s;
+  } else {
+    if ((s = cosine_keys(h, d_queries, nq, k, st))) return s;
+    if ((s = bm25_keys(h, d_terms, d_offs, nq, k, st))) return s;
+  }
   OI_CK(oi_launch_rrf(h->d_keys_cos, h->d_keys_bm25, nq, k, rrf_k, d_ids, d_rrf, d_rc, d_rb, st, &h->launches));
   return OI_OK;
 }

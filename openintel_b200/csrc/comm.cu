@@ -101,8 +101,9 @@ extern "C" oi_status oi_index_comm_init(oi_index *h, int32_t rank, int32_t world
     return h->fail(OI_ERR_COMM, "ncclCommInitRank: %s", api->GetErrorString(r));
   }
   const size_t B = h->desc.max_batch, K = h->desc.max_k;
-  if ((ce = cudaMalloc(&h->d_keys_local, B * K * sizeof(u64))) != cudaSuccess ||
-      (ce = cudaMalloc(&h->d_gather, (size_t)world_size * B * K * sizeof(u64))) != cudaSuccess) {
+  // two lists per query (cosine | BM25): the hybrid call exchanges both in one collective
+  if ((ce = cudaMalloc(&h->d_keys_local, 2 * B * K * sizeof(u64))) != cudaSuccess ||
+      (ce = cudaMalloc(&h->d_gather, 2 * (size_t)world_size * B * K * sizeof(u64))) != cudaSuccess) {
     oi_comm_destroy(h);
     return h->fail(OI_ERR_OUT_OF_MEMORY, "cudaMalloc(gather): %s", cudaGetErrorString(ce));
   }
@@ -118,6 +119,22 @@ oi_status oi_comm_gather_merge(oi_index *h, const u64 *d_local, uint32_t nq, uin
   ncclResult_t r = h->comm_skip ? ncclSuccess : api->AllGather(d_local, h->d_gather, (size_t)nq * k, ncclUint64, h->comm->comm, st);
   if (r != ncclSuccess) return h->fail(OI_ERR_COMM, "ncclAllGather: %s", api->GetErrorString(r));
   cudaError_t e = oi_launch_merge_shards(h->d_gather, (uint32_t)h->world, nq, k, d_out, st, &h->launches);
+  if (e != cudaSuccess) return h->fail(OI_ERR_CUDA, "merge_shards: %s", cudaGetErrorString(e));
+  return OI_OK;
+}
+
+// The hybrid call's exchange: d_local2 = [cosine lists nq x k | BM25 lists nq x k] of this shard; ONE all-gather
+// carries both modalities (one synchronisation point per batch instead of two: every collective waits for the
+// slowest rank), then each modality is merged from its half of every rank's block.
+oi_status oi_comm_gather_merge2(oi_index *h, const u64 *d_local2, uint32_t nq, uint32_t k, u64 *d_out_cos, u64 *d_out_bm25, cudaStream_t st) {
+  if (nq == 0) return OI_OK;
+  OiNcclApi *api = nccl_api();
+  if (!h->comm || !api->lib) return h->fail(OI_ERR_STATE, "oi_index_comm_init was not called");
+  const size_t half = (size_t)nq * k;
+  ncclResult_t r = h->comm_skip ? ncclSuccess : api->AllGather(d_local2, h->d_gather, 2 * half, ncclUint64, h->comm->comm, st);
+  if (r != ncclSuccess) return h->fail(OI_ERR_COMM, "ncclAllGather: %s", api->GetErrorString(r));
+  cudaError_t e = oi_launch_merge_shards(h->d_gather, (uint32_t)h->world, nq, k, d_out_cos, st, &h->launches, 2 * half);
+  if (e == cudaSuccess) e = oi_launch_merge_shards(h->d_gather + half, (uint32_t)h->world, nq, k, d_out_bm25, st, &h->launches, 2 * half);
   if (e != cudaSuccess) return h->fail(OI_ERR_CUDA, "merge_shards: %s", cudaGetErrorString(e));
   return OI_OK;
 }

@@ -581,11 +581,11 @@ __global__ void unpack_keys_kernel(const u64 *keys, uint32_t n, uint32_t *ids, f
 
 // One CTA per query: exact top-k of `world` sorted lists (shards after the all-gather, or the per-item lists
 // of the BM25 kernel), list r of query qi at gathered + (r * nq + qi) * k.
-__global__ void __launch_bounds__(256) merge_shards_kernel(const u64 *gathered, uint32_t world, uint32_t nq, uint32_t k, u64 *out) {
+__global__ void __launch_bounds__(256) merge_shards_kernel(const u64 *gathered, uint32_t world, size_t rank_stride, uint32_t k, u64 *out) {
   __shared__ SelState S;
   const int tid = threadIdx.x;
   const uint32_t qi = blockIdx.x;
-  merge_sorted_lists(S, gathered + (size_t)qi * k, world, (size_t)nq * k, k, tid, 256, 0);
+  merge_sorted_lists(S, gathered + (size_t)qi * k, world, rank_stride, k, tid, 256, 0);
   for (uint32_t i = tid; i < k; i += 256) out[(size_t)qi * k + i] = i < S.cnt ? S.buf[i] : 0ull;
 }
 
@@ -668,9 +668,9 @@ cudaError_t oi_launch_unpack_keys(const u64 *d_keys, uint32_t n, uint32_t *d_ids
 }
 
 cudaError_t oi_launch_merge_shards(const u64 *d_gathered, uint32_t world, uint32_t nq, uint32_t k,
-                                   u64 *d_out, cudaStream_t stream, uint64_t *launches) {
+                                   u64 *d_out, cudaStream_t stream, uint64_t *launches, size_t rank_stride) {
   if (nq == 0) return cudaSuccess;
-  merge_shards_kernel<<<nq, 256, 0, stream>>>(d_gathered, world, nq, k, d_out);
+  merge_shards_kernel<<<nq, 256, 0, stream>>>(d_gathered, world, rank_stride ? rank_stride : (size_t)nq * k, k, d_out);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -27,8 +27,8 @@ struct oi_index {
   float *d_queries = nullptr;     // [max_batch][dim]
   u64 *d_keys_cos = nullptr;      // [max_batch][max_k] global cosine lists
   u64 *d_keys_bm25 = nullptr;     // [max_batch][max_k] global BM25 lists
-  u64 *d_keys_local = nullptr;    // [max_batch][max_k] shard-local list before the all-gather
-  u64 *d_gather = nullptr;        // [world][max_batch][max_k]
+  u64 *d_keys_local = nullptr;    // 2 x [max_batch][max_k] shard-local lists before the all-gather
+  u64 *d_gather = nullptr;        // [world] x 2 x [max_batch][max_k]
   uint32_t *d_out_u32 = nullptr;  // 3 x [max_batch][max_k]
   float *d_out_f32 = nullptr;     // [max_batch][max_k]
   // small host-buffer calls go through one pinned staging block each way: one H2D copy of (queries | terms |
@@ -81,3 +81,5 @@ oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, u
 void oi_comm_destroy(oi_index *h);
 // all-gathers each rank's [nq][k] local lists and merges them into d_out [nq][k] on every rank
 oi_status oi_comm_gather_merge(oi_index *h, const u64 *d_local, uint32_t nq, uint32_t k, u64 *d_out, cudaStream_t st);
+// hybrid: d_local2 = [cosine nq x k | BM25 nq x k]; one all-gather, two merges
+oi_status oi_comm_gather_merge2(oi_index *h, const u64 *d_local2, uint32_t nq, uint32_t k, u64 *d_out_cos, u64 *d_out_bm25, cudaStream_t st);
