@@ -176,6 +176,10 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->gemm_sample_tiles = (int)value;
     return OI_OK;
   }
+  if (!strcmp(name, "no_pinned_staging")) {
+    h->no_pinned_staging = (int)value;
+    return OI_OK;
+  }
   if (!strcmp(name, "comm_debug_skip_gather")) {
     h->comm_skip = (int)value;
     return OI_OK;
@@ -303,7 +307,7 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = h->stream;
   const size_t qbytes = (size_t)nq * h->desc.dim * sizeof(float), n = (size_t)nq * k;
-  if (qbytes <= OI_PIN_BYTES && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
+  if (!h->no_pinned_staging && qbytes <= OI_PIN_BYTES && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
     memcpy(h->h_pin_in, queries, qbytes);
     OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, qbytes, cudaMemcpyHostToDevice, st));
     if ((s = cosine_keys(h, reinterpret_cast<const float *>(h->d_pin_in), nq, k, st))) return s;
@@ -420,7 +424,7 @@ extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const 
   const size_t n = (size_t)nq * k;
   size_t o_offs, o_terms;
   const size_t in_bytes = pin_in_layout(0, nq, q_offsets[nq], &o_offs, &o_terms);
-  if (in_bytes && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
+  if (!h->no_pinned_staging && in_bytes && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
     memcpy(h->h_pin_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
     if (q_offsets[nq]) memcpy(h->h_pin_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);
     OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, in_bytes, cudaMemcpyHostToDevice, st));
@@ -492,7 +496,7 @@ extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const u
   if ((s = check_terms(h, q_terms, q_offsets, nq))) return s;
   size_t o_offs, o_terms;
   const size_t in_bytes = pin_in_layout(qbytes, nq, q_offsets[nq], &o_offs, &o_terms);
-  if (in_bytes && n * 16 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
+  if (!h->no_pinned_staging && in_bytes && n * 16 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
     memcpy(h->h_pin_in, queries, qbytes);
     memcpy(h->h_pin_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
     if (q_offsets[nq]) memcpy(h->h_pin_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);

@@ -6,19 +6,24 @@
 //
 // Scoring kernel (bm25_blocked_kernel), the hot path of BASELINE config 3:
 //   * a work item is (query q, super-range s of documents); items are handed out from an atomic
-//     counter, s-major, so that the groups running at the same time walk the same part of every
-//     posting list and the second reader of a posting finds it in L1/L2 instead of HBM.
-//   * a *group* (32..512 threads of a 512-thread CTA) owns one item at a time.  It walks its
-//     super-range block by block (R documents per block); the block's scores live in shared
-//     memory (acc[R] f32), so the dense score vector never exists in HBM.
-//   * per block, the query's DISTINCT terms are applied in ascending term id (SPEC order).  A
-//     posting list holds a document at most once, so one term pass has no write conflicts and
-//     needs no atomics; passes are separated by a group barrier.  Posting lists are read as
-//     128-posting chunks (coalesced 4 B doc id + 4 B weight), software-pipelined one chunk ahead.
-//   * after the last term the group scans acc[] once: every positive score whose key beats the
-//     running threshold goes to the group's candidate buffer (filter + buffer selection, the
-//     same scheme as the cosine scan), acc[] is zeroed for the next block, and the k-th best key
-//     is published grid-wide (atomicMax) so later blocks of the same query filter harder.
+//     counter, s-major, ~24 per warp, so that the warps running at the same time walk the same part
+//     of every posting list (the second reader of a posting finds it in L2) and the last items to
+//     finish leave the SMs idle for a small part of the launch.
+//   * one WARP owns an item.  It walks its super-range block by block (R = 2048 documents); the
+//     block's scores live in shared memory (acc[R] f32), so the dense score vector never exists in HBM.
+//   * the query's term table lives in registers (lane l = term l): one ballot finds the lists with
+//     postings in the block, one min-reduction the next block with any posting.
+//   * per block, the query's DISTINCT terms are applied in ascending term id (SPEC order).  A posting
+//     list holds a document at most once, so one term pass has no write conflicts and needs no
+//     atomics.  Sparse lists: the first 64-posting chunk of every present list is requested at block
+//     start with one bulk copy per list (cp.async.bulk, all in flight at once, per-warp mbarrier).
+//     Dense terms (>= 1/16 of the documents) add a weight column, two columns per sweep, and a dense
+//     first pass only stores, so the block is never cleared.
+//   * after the last term the warp scans acc[] once: every positive score whose key beats the
+//     running threshold goes to the warp's candidate buffer (filter + buffer selection, the same
+//     scheme as the cosine scan), and the k-th best key is published grid-wide (atomicMax) so later
+//     blocks of the same query filter harder.  A block scanned without any threshold takes the k-th
+//     largest of its 256 group maxima as a bound first.
 //   * the item ends with a sorted k-list per (query, super-range); bm25 merge = one CTA per
 //     query over the S lists.
 //

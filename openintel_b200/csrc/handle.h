@@ -35,6 +35,7 @@ struct oi_index {
   // offsets) and one D2H copy of (ids | scores | ranks) instead of 3 + 4 copies from / to pageable memory
   unsigned char *h_pin_in = nullptr, *h_pin_out = nullptr;  // OI_PIN_BYTES each (cudaHostAlloc)
   unsigned char *d_pin_in = nullptr, *d_pin_out = nullptr;  // device mirrors
+  int no_pinned_staging = 0;  // tests: take the large-call path (direct copies from / to the caller's buffers)
 
   // batched cosine on the tensor cores (cosine_gemm.cu); workspace is created on first use
   OiGemm *gemm = nullptr;

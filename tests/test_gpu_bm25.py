@@ -222,6 +222,27 @@ def test_hybrid_matches_oracle(oi, k):
             assert np.array_equal(ids[j], e_ids) and np.array_equal(rrf[j].view(np.uint32), e_val.view(np.uint32))
 
 
+def test_host_buffer_copy_paths_agree(oi):
+    """small host-buffer calls go through one pinned staging block each way, large ones copy from / to the caller's
+    buffers directly: same results either way (cosine, BM25, hybrid; ragged term lists)"""
+    n, dim, vocab, k, nq = 20000, 128, 2000, 25, 9
+    corp = O.synth_bm25_corpus(n, vocab)
+    qv = O.synth_rows_f32(nq, dim, stream=1)
+    qt = [list(map(int, t[: 1 + j % 8])) for j, t in enumerate(O.synth_query_terms(nq, 8, corp["cdf"]))]
+    qt[4] = []
+    with oi.GpuIndex(n_docs=n, dim=dim, max_k=k, max_batch=nq) as ix:
+        ix.synth_embeddings(O.SEED)
+        ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.bm25_finalize()
+        res = []
+        for off in (0, 1):
+            ix.set_option("no_pinned_staging", off)
+            res.append((ix.search_cosine(qv, k), ix.search_bm25(qt, k), ix.search_hybrid(qv, qt, k)))
+    for a, b in zip(res[0], res[1]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
 def test_rrf_short_and_disjoint_lists(oi):
     """BM25 list shorter than k (padding) and a query with no lexical match at all."""
     n, dim, vocab, k = 4000, 128, 50000, 30
