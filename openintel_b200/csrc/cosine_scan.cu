@@ -263,6 +263,133 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_ldg_kernel(co
   scan_epilogue(S, p, tid, kConsumerThreads, 0);
 }
 
+// =================================================================================================
+// Multi-query scan: one pass over the matrix serves a GROUP of up to kMultiQ queries (f32 indexes have no
+// tensor-core path -- tf32 products would miss the 1e-5 tolerance -- and bf16 batches below the GEMM threshold
+// land here too).  Same structure as variant 0 (direct 128-bit loads, 2 CTAs per SM, contiguous row ranges);
+// the group's queries sit in registers, every loaded row vector is used kMultiQ times, and the kMultiQ x 2
+// partial sums of a row pair are reduced together: a butterfly that halves the number of live values at each of
+// its first three steps (9 shuffles instead of 40).  One selection state per query in dynamic shared memory;
+// the per-query epilogue (publish, last-CTA merge) is the single-query one.  The bytes stay the bound: per row
+// 3 loads, 48 FMAs and ~5 shuffles per lane at dim 384, ~20 issue cycles per row and SM against ~50 of HBM time.
+// =================================================================================================
+constexpr int kMultiQ = 4;
+
+template <typename T, int NVL>
+__global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_multi_kernel(const OiScanParams p) {
+  constexpr int QF = Elem<T>::QF;
+  constexpr int ROWS = 2;
+  extern __shared__ __align__(16) unsigned char s_multi[];
+  SelState *S = reinterpret_cast<SelState *>(s_multi);  // [kMultiQ]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ng = p.nq;  // queries in this group, 1..kMultiQ (CTA-uniform)
+
+  float q[kMultiQ][NVL][QF];
+#pragma unroll
+  for (int g = 0; g < kMultiQ; ++g)
+#pragma unroll
+    for (int j = 0; j < NVL; ++j) {
+      const uint32_t v = lane + 32 * j;
+      if ((uint32_t)g < ng && v < p.nv) {
+        Elem<T>::load_q(p.q + (size_t)g * p.dim, v, q[g][j]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < QF; ++e) q[g][j][e] = 0.0f;
+      }
+    }
+  if (tid < kMultiQ) { S[tid].cnt = 0; S[tid].thr = 0ull; }
+  __syncthreads();
+
+  const uint32_t row_begin = min(p.n_rows, blockIdx.x * p.rows_per_cta);
+  const uint32_t row_end = min(p.n_rows, row_begin + p.rows_per_cta);
+  const uint4 *mat = p.mat;
+  const uint32_t nv = p.nv;
+  // after the butterfly, lanes 4i .. 4i+3 hold value i = query (i >> 1), row (i & 1) of the pair
+  const int my_val = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const int my_g = my_val >> 1, my_i = my_val & 1;
+
+  uint32_t base = row_begin;
+  while (base < row_end) {
+    // super-iteration: at most (CAP - cnt) rows for the fullest buffer, so pushes cannot overflow any of them
+    uint32_t room = OI_SEL_CAP;
+    for (uint32_t g = 0; g < ng; ++g) room = min(room, (uint32_t)OI_SEL_CAP - S[g].cnt);
+    const u64 my_thr = (uint32_t)my_g < ng ? max(S[my_g].thr, ld_relaxed_u64(p.gthr + my_g)) : ~0ull;
+    const uint32_t stop = base + min(row_end - base, room);
+    __syncthreads();  // (cnt, thr) snapshots are CTA-uniform before anybody pushes
+    for (uint32_t r0 = base + warp * ROWS; r0 < stop; r0 += kConsumerWarps * ROWS) {
+      uint4 d[ROWS][NVL];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        const uint4 *rp = mat + (size_t)(r0 + i) * nv;
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+          const uint32_t v = lane + 32 * j;
+          d[i][j] = (r0 + i < stop && v < nv) ? oi_ldg_stream(rp + v) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      float v8[kMultiQ * ROWS];
+#pragma unroll
+      for (int g = 0; g < kMultiQ; ++g)
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          float a = 0.0f;
+#pragma unroll
+          for (int j = 0; j < NVL; ++j) a = Elem<T>::dot(d[i][j], q[g][j], a);
+          v8[g * ROWS + i] = a;
+        }
+      float v4[4], v2[2];
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float send = hi ? v8[j] : v8[j + 4], keep = hi ? v8[j + 4] : v8[j];
+          v4[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+        }
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float send = hi ? v4[j] : v4[j + 2], keep = hi ? v4[j + 2] : v4[j];
+          v2[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
+        }
+      }
+      float v1;
+      {
+        const bool hi = lane & 4;
+        const float send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
+        v1 = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+      }
+      v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 2);
+      v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 1);
+      if ((lane & 3) == 0 && r0 + my_i < stop) {
+        const u64 key = oi_make_key(v1, p.doc_base + r0 + my_i);
+        if (key > my_thr) oi_sel_push(S[my_g].buf, &S[my_g].cnt, key);
+      }
+    }
+    base = stop;
+    __syncthreads();
+    if (base < row_end) {
+      for (uint32_t g = 0; g < ng; ++g) {
+        if (S[g].cnt > OI_SEL_CAP / 2) {  // CTA-uniform: read after the barrier
+          oi_sel_compact(S[g].buf, &S[g].cnt, &S[g].thr, p.k, tid, kConsumerThreads, 0);
+          if (tid == 0 && S[g].cnt == p.k) atomicMax(p.gthr + g, S[g].thr);
+        }
+      }
+    }
+  }
+  for (uint32_t g = 0; g < ng; ++g) {
+    OiScanParams pq = p;
+    pq.cand = p.cand + (size_t)g * p.cand_stride;
+    pq.gthr = p.gthr + g;
+    pq.ticket = p.ticket + g;
+    pq.tile_ctr = p.tile_ctr + g;
+    pq.out_keys = p.out_keys + (size_t)g * p.k;
+    scan_epilogue(S[g], pq, tid, kConsumerThreads, 0);
+    __syncthreads();
+  }
+}
+
 // Generic fallback for wide rows (nv > 256): the query lives in shared memory as f32.
 template <typename T>
 __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_generic_kernel(const OiScanParams p) {
@@ -571,6 +698,29 @@ cudaError_t dispatch_bulk(const OiScanParams &p, uint32_t grid, cudaStream_t st)
   }
 }
 
+template <typename T>
+cudaError_t launch_multi(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
+  const size_t smem = (size_t)kMultiQ * sizeof(SelState);
+  const uint32_t nvl = (p.nv + 31) / 32;
+  cudaError_t e;
+  switch (nvl) {
+    case 1:
+      if ((e = cudaFuncSetAttribute(cosine_scan_multi_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      cosine_scan_multi_kernel<T, 1><<<grid, kConsumerThreads, smem, st>>>(p);
+      break;
+    case 2:
+      if ((e = cudaFuncSetAttribute(cosine_scan_multi_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      cosine_scan_multi_kernel<T, 2><<<grid, kConsumerThreads, smem, st>>>(p);
+      break;
+    case 3:
+      if ((e = cudaFuncSetAttribute(cosine_scan_multi_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      cosine_scan_multi_kernel<T, 3><<<grid, kConsumerThreads, smem, st>>>(p);
+      break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 __global__ void unpack_keys_kernel(const u64 *keys, uint32_t n, uint32_t *ids, float *scores) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -596,7 +746,7 @@ uint32_t oi_cosine_scan_max_grid(int num_sms) { return (uint32_t)num_sms * 2u; }
 cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_rows, uint32_t dim,
                                   uint32_t doc_base, const float *d_queries, uint32_t nq, uint32_t k,
                                   const OiCosineWorkspace &ws, u64 *d_out_keys, int variant, int num_sms,
-                                  cudaStream_t stream, uint64_t *launches) {
+                                  cudaStream_t stream, uint64_t *launches, bool multi_query) {
   const uint32_t esize = dtype == OI_DTYPE_F32 ? 4u : 2u;
   OiScanParams p;
   p.mat = reinterpret_cast<const uint4 *>(d_mat);
@@ -605,6 +755,32 @@ cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_
   p.nv = dim * esize / 16u;
   p.doc_base = doc_base;
   p.k = k;
+  if (multi_query && nq >= 2 && p.nv <= 96) {
+    // groups of kMultiQ queries share one pass over the matrix (cosine_scan_multi_kernel)
+    uint32_t grid = (uint32_t)num_sms * 2u;
+    const uint32_t max_useful = (uint32_t)((n_rows + 63) / 64);
+    if (grid > max_useful) grid = max_useful ? max_useful : 1;
+    if (grid > ws.max_grid) grid = ws.max_grid;
+    uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
+    rpc = (rpc + 31u) & ~31u;
+    p.rows_per_cta = rpc;
+    grid = (uint32_t)((n_rows + rpc - 1) / rpc);
+    if (grid == 0) grid = 1;
+    p.cand_stride = ws.max_grid * ws.k_stride;
+    for (uint32_t g0 = 0; g0 < nq; g0 += kMultiQ) {
+      p.nq = nq - g0 < (uint32_t)kMultiQ ? nq - g0 : (uint32_t)kMultiQ;
+      p.q = d_queries + (size_t)g0 * dim;
+      p.cand = ws.cand + (size_t)g0 * p.cand_stride;
+      p.gthr = ws.gthr + g0;
+      p.ticket = ws.ticket + g0;
+      p.tile_ctr = ws.tile_ctr + g0;
+      p.out_keys = d_out_keys + (size_t)g0 * k;
+      cudaError_t e = dtype == OI_DTYPE_F32 ? launch_multi<float>(p, grid, stream) : launch_multi<__nv_bfloat16>(p, grid, stream);
+      if (e != cudaSuccess) return e;
+      if (launches) ++*launches;
+    }
+    return cudaSuccess;
+  }
   const bool bulk = variant == 1 && p.nv <= 256;
   uint32_t grid;
   if (bulk) {

@@ -37,6 +37,7 @@ def test_cosine_f32_parity(oi, variant, n, dim, k):
     with oi.GpuIndex(n_docs=n, dim=dim, max_k=k, max_batch=4) as ix:
         ix.load_embeddings(rows)
         ix.set_option("cosine_variant", variant)
+        ix.set_option("cosine_multi_query", 0)  # the single-query kernels; the multi-query scan has its own test
         ids, sc = ix.search_cosine(qs, k)
     for j in range(4):
         allsc = O.cosine_scores_f32(rows, qs[j])
@@ -52,6 +53,7 @@ def test_cosine_bf16_parity(oi, variant, n, dim, k):
     with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=3, doc_base=7) as ix:
         ix.load_embeddings(rows)
         ix.set_option("cosine_variant", variant)
+        ix.set_option("cosine_multi_query", 0)
         ids, sc = ix.search_cosine(qs, k)
     for j in range(3):
         allsc = O.cosine_scores_bf16(rows, qs[j])
@@ -59,6 +61,38 @@ def test_cosine_bf16_parity(oi, variant, n, dim, k):
         assert_ranked_close(ids[j], sc[j], wi, ws, allsc, BF16_TOL, doc_base=7)
         # measured error is far inside the budget
         assert np.max(np.abs(sc[j] - ws)) < 1e-5
+
+
+@pytest.mark.parametrize("n,dim,bf16,k,nq", [(50000, 384, False, 100, 9), (30011, 256, False, 10, 4), (4097, 64, False, 1, 2),
+                                             (70000, 128, False, 1000, 5), (40000, 768, True, 100, 3), (9000, 128, True, 7, 6),
+                                             (3, 64, False, 5, 7)])
+def test_cosine_multi_query_scan_parity(oi, n, dim, bf16, k, nq):
+    """calls with several queries share one matrix pass per group of 4 (rows of at most 1536 bytes): every query's
+    list must match the oracle and the single-query kernel; the last group may be partial, shards may be ragged"""
+    rows = O.synth_rows_bf16(n, dim) if bf16 else O.synth_rows_f32(n, dim)
+    n_pl = min(2, nq)
+    qs = np.concatenate([O.synth_rows_f32(nq - n_pl, dim, stream=1), O.synth_planted_queries(n_pl, dim, n)[0]]) if n >= 100 \
+        else O.synth_rows_f32(nq, dim, stream=1)
+    with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16 if bf16 else oi.DTYPE_F32, max_k=k, max_batch=nq, doc_base=5) as ix:
+        ix.load_embeddings(rows)
+        ix.set_option("cosine_gemm_min_batch", 0)  # bf16 batches would otherwise take the tensor-core path
+        l0 = ix.launch_count()
+        ids, sc = ix.search_cosine(qs, k)
+        multi_launches = ix.launch_count() - l0
+        ix.set_option("cosine_multi_query", 0)
+        ids1, sc1 = ix.search_cosine(qs, k)
+    assert multi_launches == (nq + 3) // 4 + 1  # one scan per group of 4 + the unpack kernel
+    tol = BF16_TOL if bf16 else F32_TOL
+    for j in range(nq):
+        allsc = O.cosine_scores_bf16(rows, qs[j]) if bf16 else O.cosine_scores_f32(rows, qs[j])
+        wi, ws, _ = O.topk_f64(allsc, k, doc_base=5)
+        kk = min(k, n)
+        assert_ranked_close(ids[j][:kk], sc[j][:kk], wi[:kk], ws[:kk], allsc, tol, doc_base=5)
+        assert np.all(ids[j][kk:] == oi.NO_DOC) and np.all(sc[j][kk:] == 0)
+        # against the single-query kernel: same documents unless two scores tie within the f32 summation noise
+        if not np.array_equal(ids[j], ids1[j]):
+            assert sorted(ids[j].tolist()) == sorted(ids1[j].tolist()) or np.max(np.abs(sc[j] - sc1[j])) < 1e-6
+        assert np.allclose(sc[j], sc1[j], rtol=0, atol=2e-6)
 
 
 @pytest.mark.parametrize("variant", [0, 1])
