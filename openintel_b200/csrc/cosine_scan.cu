@@ -224,17 +224,29 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_ldg_kernel(co
     const u64 thr = max(S.thr, ld_relaxed_u64(p.gthr));
     const uint32_t stop = base + span;
     __syncthreads();  // (cnt, thr) snapshot is CTA-uniform before anybody pushes
-    for (uint32_t r0 = base + warp * ROWS; r0 < stop; r0 += kConsumerWarps * ROWS) {
-      uint4 d[ROWS][NVL];
+    // the loads of the next row pair are in flight while this one is reduced (one pair of look-ahead per warp)
+    uint4 dn[ROWS][NVL];
+    {
+      const uint32_t r0 = base + warp * ROWS;
 #pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const uint4 *rp = mat + (size_t)(r0 + i) * nv;
+      for (int i = 0; i < ROWS; ++i)
 #pragma unroll
         for (int j = 0; j < NVL; ++j) {
           const uint32_t v = lane + 32 * j;
-          d[i][j] = (r0 + i < stop && v < nv) ? oi_ldg_stream(rp + v) : make_uint4(0, 0, 0, 0);
+          dn[i][j] = (r0 + i < stop && v < nv) ? oi_ldg_stream(mat + (size_t)(r0 + i) * nv + v) : make_uint4(0, 0, 0, 0);
         }
-      }
+    }
+    for (uint32_t r0 = base + warp * ROWS; r0 < stop; r0 += kConsumerWarps * ROWS) {
+      uint4 d[ROWS][NVL];
+      const uint32_t rn = r0 + kConsumerWarps * ROWS;
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i)
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+          const uint32_t v = lane + 32 * j;
+          d[i][j] = dn[i][j];
+          dn[i][j] = (rn + i < stop && v < nv) ? oi_ldg_stream(mat + (size_t)(rn + i) * nv + v) : make_uint4(0, 0, 0, 0);
+        }
       float acc[ROWS];
 #pragma unroll
       for (int i = 0; i < ROWS; ++i) {
@@ -308,25 +320,43 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_multi_kernel(
   const int my_val = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const int my_g = my_val >> 1, my_i = my_val & 1;
 
+  // The first super-iterations are short (128, 256, 512, ... rows) and a buffer is cut to its best k as soon as it
+  // holds 2k keys: the first thresholds then come from sorts of a few hundred keys.  (Scanning 2048 rows without
+  // a threshold and sorting 2048 keys per query cost a third of the pass.)
+  uint32_t span_cap = 128;
+  const uint32_t ctrig = min((uint32_t)OI_SEL_CAP / 2, max(2u * p.k, 128u));
   uint32_t base = row_begin;
   while (base < row_end) {
     // super-iteration: at most (CAP - cnt) rows for the fullest buffer, so pushes cannot overflow any of them
-    uint32_t room = OI_SEL_CAP;
+    uint32_t room = span_cap;
+    span_cap = min(span_cap * 2, (uint32_t)OI_SEL_CAP);
     for (uint32_t g = 0; g < ng; ++g) room = min(room, (uint32_t)OI_SEL_CAP - S[g].cnt);
     const u64 my_thr = (uint32_t)my_g < ng ? max(S[my_g].thr, ld_relaxed_u64(p.gthr + my_g)) : ~0ull;
     const uint32_t stop = base + min(row_end - base, room);
     __syncthreads();  // (cnt, thr) snapshots are CTA-uniform before anybody pushes
-    for (uint32_t r0 = base + warp * ROWS; r0 < stop; r0 += kConsumerWarps * ROWS) {
-      uint4 d[ROWS][NVL];
+    // the loads of the next row pair are in flight while this one is reduced (one pair of look-ahead per warp)
+    uint4 dn[ROWS][NVL];
+    {
+      const uint32_t r0 = base + warp * ROWS;
 #pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const uint4 *rp = mat + (size_t)(r0 + i) * nv;
+      for (int i = 0; i < ROWS; ++i)
 #pragma unroll
         for (int j = 0; j < NVL; ++j) {
           const uint32_t v = lane + 32 * j;
-          d[i][j] = (r0 + i < stop && v < nv) ? oi_ldg_stream(rp + v) : make_uint4(0, 0, 0, 0);
+          dn[i][j] = (r0 + i < stop && v < nv) ? oi_ldg_stream(mat + (size_t)(r0 + i) * nv + v) : make_uint4(0, 0, 0, 0);
         }
-      }
+    }
+    for (uint32_t r0 = base + warp * ROWS; r0 < stop; r0 += kConsumerWarps * ROWS) {
+      uint4 d[ROWS][NVL];
+      const uint32_t rn = r0 + kConsumerWarps * ROWS;
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i)
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+          const uint32_t v = lane + 32 * j;
+          d[i][j] = dn[i][j];
+          dn[i][j] = (rn + i < stop && v < nv) ? oi_ldg_stream(mat + (size_t)(rn + i) * nv + v) : make_uint4(0, 0, 0, 0);
+        }
       float v8[kMultiQ * ROWS];
 #pragma unroll
       for (int g = 0; g < kMultiQ; ++g)
@@ -371,7 +401,7 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_multi_kernel(
     __syncthreads();
     if (base < row_end) {
       for (uint32_t g = 0; g < ng; ++g) {
-        if (S[g].cnt > OI_SEL_CAP / 2) {  // CTA-uniform: read after the barrier
+        if (S[g].cnt > ctrig) {  // CTA-uniform: read after the barrier
           oi_sel_compact(S[g].buf, &S[g].cnt, &S[g].thr, p.k, tid, kConsumerThreads, 0);
           if (tid == 0 && S[g].cnt == p.k) atomicMax(p.gthr + g, S[g].thr);
         }
