@@ -150,7 +150,7 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     return OI_OK;
   }
   if (!strcmp(name, "cosine_multi_query")) {
-    OI_REQUIRE(value == 0 || value == 1, "cosine_multi_query must be 0 (every query scans the matrix on its own) or 1");
+    OI_REQUIRE(value >= 0 && value <= 2, "cosine_multi_query must be 0 (every query scans the matrix on its own), 1 (direct loads) or 2 (bulk-copy pipeline)");
     h->cosine_multi_query = (int)value;
     return OI_OK;
   }
@@ -281,7 +281,7 @@ static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, u
     if (s) return s;
   } else {
     OI_CK(oi_launch_cosine_scan(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, (uint32_t)h->desc.doc_base, d_queries, nq, k,
-                                h->cws, local, h->cosine_variant, h->num_sms, st, &h->launches, h->cosine_multi_query != 0));
+                                h->cws, local, h->cosine_variant, h->num_sms, st, &h->launches, h->cosine_multi_query));
   }
   if (h->world > 1 && !local_only) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_cos, st);
   return OI_OK;

@@ -649,6 +649,182 @@ __global__ void __launch_bounds__(kBulkBlock, 1)
   }
 }
 
+// =================================================================================================
+// Multi-query scan on the bulk-copy pipeline: the producer warp of variant 1 (dynamic tiles, cp.async.bulk ring)
+// feeds 16 consumer warps that hold a GROUP of kMultiQ queries in registers; selection states and epilogue as in
+// cosine_scan_multi_kernel (no epilogue overlap: the group's queries finish together).  The copy engine keeps the
+// ring full whatever the consumers do, which the direct-load version cannot (its loads stop during every sort).
+// Dynamic smem: [n_stages][tile_bytes] | full[n_stages], empty[n_stages] | s_tile[n_stages] | SelState[kMultiQ].
+// =================================================================================================
+constexpr int kBMBlock = kBulkThreads + 32;
+
+template <typename T, int NVL>
+__global__ void __launch_bounds__(kBMBlock, 1)
+    cosine_scan_bulk_multi_kernel(const OiScanParams p, const uint32_t tile_rows, const uint32_t n_stages) {
+  constexpr int QF = Elem<T>::QF;
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t row_bytes = p.nv * 16u;
+  const uint32_t tile_bytes = tile_rows * row_bytes;
+  u64 *full = reinterpret_cast<u64 *>(s_dyn + (size_t)n_stages * tile_bytes);
+  u64 *empty = full + n_stages;
+  uint32_t *s_tile = reinterpret_cast<uint32_t *>(empty + n_stages);
+  SelState *S = reinterpret_cast<SelState *>(s_dyn + (((size_t)n_stages * tile_bytes + n_stages * 20u + 15u) & ~(size_t)15));
+  const uint32_t n_tiles = (p.n_rows + tile_rows - 1) / tile_rows;
+  const uint32_t ng = p.nq;  // queries in this group, 1..kMultiQ
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < n_stages; ++s) { oi_mbar_init(&full[s], 1); oi_mbar_init(&empty[s], kBulkWarps); }
+    for (int g = 0; g < kMultiQ; ++g) { S[g].cnt = 0; S[g].thr = 0ull; }
+    oi_mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kBulkWarps) {
+    // ---------------- producer: one elected lane, one pass over the shard's tiles ----------------
+    if (lane == 0) {
+      const u64 policy = oi_policy_evict_first();
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(p.mat);
+      uint32_t *ctr = p.tile_ctr;
+      uint32_t t = atomicAdd(ctr, 1u);
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+        const uint32_t t_next = t < n_tiles ? atomicAdd(ctr, 1u) : kTileEnd;  // ticket for the next round
+        oi_mbar_wait(&empty[s], ph ^ 1u);
+        if (t >= n_tiles) {
+          s_tile[s] = kTileEnd;
+          oi_mbar_arrive(&full[s]);
+          break;
+        }
+        s_tile[s] = t;
+        const uint32_t rows = min(tile_rows, p.n_rows - t * tile_rows);
+        const uint32_t bytes = rows * row_bytes;
+        oi_mbar_expect_tx(&full[s], bytes);
+        oi_bulk_g2s(s_dyn + (size_t)s * tile_bytes, src + (size_t)t * tile_bytes, bytes, &full[s], policy);
+        t = t_next;
+      }
+    }
+    return;  // the producer warp takes no part in barrier 1 or the epilogues
+  }
+
+  // -------------------------------- consumers --------------------------------------------------
+  float q[kMultiQ][NVL][QF];
+#pragma unroll
+  for (int g = 0; g < kMultiQ; ++g)
+#pragma unroll
+    for (int j = 0; j < NVL; ++j) {
+      const uint32_t v = lane + 32 * j;
+      if ((uint32_t)g < ng && v < p.nv) {
+        Elem<T>::load_q(p.q + (size_t)g * p.dim, v, q[g][j]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < QF; ++e) q[g][j][e] = 0.0f;
+      }
+    }
+  const int my_val = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const int my_g = my_val >> 1, my_i = my_val & 1;
+  const uint32_t ctrig = min((uint32_t)OI_SEL_CAP / 2, max(2u * p.k, 128u));
+  const uint32_t max_tiles = max(1u, (uint32_t)OI_SEL_CAP / tile_rows);
+  uint32_t tiles_cap = max(1u, 128u / tile_rows);  // short first super-iterations: early, cheap thresholds
+  uint32_t it = 0;
+  bool done = false;
+  while (!done) {
+    uint32_t room = OI_SEL_CAP;
+    for (uint32_t g = 0; g < ng; ++g) room = min(room, (uint32_t)OI_SEL_CAP - S[g].cnt);
+    const uint32_t tiles_now = max(1u, min(tiles_cap, room / tile_rows));
+    tiles_cap = min(tiles_cap * 2, max_tiles);
+    const u64 my_thr = (uint32_t)my_g < ng ? max(S[my_g].thr, ld_relaxed_u64(p.gthr + my_g)) : ~0ull;
+    oi_bar_sync(1, kBulkThreads);  // (cnt, thr) snapshots are uniform before anybody pushes
+    for (uint32_t n = 0; n < tiles_now; ++n) {
+      const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+      oi_mbar_wait(&full[s], ph);
+      const uint32_t t = s_tile[s];
+      ++it;
+      if (t == kTileEnd) {  // every consumer warp sees the same sentinel; the slot holds no data
+        __syncwarp();
+        if (lane == 0) oi_mbar_arrive(&empty[s]);
+        done = true;
+        break;
+      }
+      const uint32_t tile_row0 = t * tile_rows;
+      const uint32_t rows = min(tile_rows, p.n_rows - tile_row0);
+      const unsigned char *tile = s_dyn + (size_t)s * tile_bytes;
+      for (uint32_t r = warp * 2; r < rows; r += kBulkWarps * 2) {
+        const uint4 *rp0 = reinterpret_cast<const uint4 *>(tile + (size_t)r * row_bytes);
+        const bool two = r + 1 < rows;
+        const uint4 *rp1 = two ? reinterpret_cast<const uint4 *>(tile + (size_t)(r + 1) * row_bytes) : rp0;
+        uint4 d[2][NVL];
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+          const uint32_t v = lane + 32 * j;
+          d[0][j] = v < p.nv ? rp0[v] : make_uint4(0, 0, 0, 0);
+          d[1][j] = v < p.nv ? rp1[v] : make_uint4(0, 0, 0, 0);
+        }
+        float v8[kMultiQ * 2];
+#pragma unroll
+        for (int g = 0; g < kMultiQ; ++g)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NVL; ++j) a = Elem<T>::dot(d[i][j], q[g][j], a);
+            v8[g * 2 + i] = a;
+          }
+        float v4[4], v2[2];
+        {
+          const bool hi = lane & 16;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float send = hi ? v8[j] : v8[j + 4], keep = hi ? v8[j + 4] : v8[j];
+            v4[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+          }
+        }
+        {
+          const bool hi = lane & 8;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float send = hi ? v4[j] : v4[j + 2], keep = hi ? v4[j + 2] : v4[j];
+            v2[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
+          }
+        }
+        float v1;
+        {
+          const bool hi = lane & 4;
+          const float send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
+          v1 = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+        }
+        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 2);
+        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 1);
+        if ((lane & 3) == 0 && (my_i == 0 || two)) {
+          const u64 key = oi_make_key(v1, p.doc_base + tile_row0 + r + (uint32_t)my_i);
+          if (key > my_thr) oi_sel_push(S[my_g].buf, &S[my_g].cnt, key);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) oi_mbar_arrive(&empty[s]);
+    }
+    oi_bar_sync(1, kBulkThreads);
+    if (!done) {
+      for (uint32_t g = 0; g < ng; ++g) {
+        if (S[g].cnt > ctrig) {  // uniform over the consumers: read after the barrier
+          oi_sel_compact(S[g].buf, &S[g].cnt, &S[g].thr, p.k, tid, kBulkThreads, 1);
+          if (tid == 0 && S[g].cnt == p.k) atomicMax(p.gthr + g, S[g].thr);
+        }
+      }
+    }
+  }
+  for (uint32_t g = 0; g < ng; ++g) {
+    OiScanParams pq = p;
+    pq.cand = p.cand + (size_t)g * p.cand_stride;
+    pq.gthr = p.gthr + g;
+    pq.ticket = p.ticket + g;
+    pq.tile_ctr = p.tile_ctr + g;
+    pq.out_keys = p.out_keys + (size_t)g * p.k;
+    scan_epilogue(S[g], pq, tid, kBulkThreads, 1);
+    oi_bar_sync(1, kBulkThreads);
+  }
+}
+
 // ---- host-side dispatch -------------------------------------------------------------------------
 template <typename T, int NVL, int ROWS>
 cudaError_t launch_ldg(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
@@ -728,6 +904,39 @@ cudaError_t dispatch_bulk(const OiScanParams &p, uint32_t grid, cudaStream_t st)
   }
 }
 
+// bulk-multi: the variant-1 tile shape with the ring cut down to leave room for kMultiQ selection states
+static inline bool bulk_multi_shape(uint32_t row_bytes, uint32_t *tile_rows, uint32_t *n_stages, size_t *smem) {
+  uint32_t tr = (49152u / row_bytes) & ~31u;
+  if (tr < 32) return false;
+  if (tr > 256) tr = 256;
+  const size_t sel = (size_t)kMultiQ * sizeof(SelState);
+  uint32_t ns = (uint32_t)((227u * 1024u - sel - 512u) / ((size_t)tr * row_bytes));
+  if (ns > 8) ns = 8;
+  if (ns < 2) return false;
+  *tile_rows = tr;
+  *n_stages = ns;
+  *smem = (((size_t)ns * tr * row_bytes + ns * 20u + 15u) & ~(size_t)15) + sel;
+  return true;
+}
+
+template <typename T, int NVL>
+cudaError_t launch_bulk_multi_n(const OiScanParams &p, uint32_t grid, uint32_t tile_rows, uint32_t n_stages, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cosine_scan_bulk_multi_kernel<T, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cosine_scan_bulk_multi_kernel<T, NVL><<<grid, kBMBlock, smem, st>>>(p, tile_rows, n_stages);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_bulk_multi(const OiScanParams &p, uint32_t grid, uint32_t tile_rows, uint32_t n_stages, size_t smem, cudaStream_t st) {
+  switch ((p.nv + 31) / 32) {
+    case 1: return launch_bulk_multi_n<T, 1>(p, grid, tile_rows, n_stages, smem, st);
+    case 2: return launch_bulk_multi_n<T, 2>(p, grid, tile_rows, n_stages, smem, st);
+    case 3: return launch_bulk_multi_n<T, 3>(p, grid, tile_rows, n_stages, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 template <typename T>
 cudaError_t launch_multi(const OiScanParams &p, uint32_t grid, cudaStream_t st) {
   const size_t smem = (size_t)kMultiQ * sizeof(SelState);
@@ -776,7 +985,7 @@ uint32_t oi_cosine_scan_max_grid(int num_sms) { return (uint32_t)num_sms * 2u; }
 cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_rows, uint32_t dim,
                                   uint32_t doc_base, const float *d_queries, uint32_t nq, uint32_t k,
                                   const OiCosineWorkspace &ws, u64 *d_out_keys, int variant, int num_sms,
-                                  cudaStream_t stream, uint64_t *launches, bool multi_query) {
+                                  cudaStream_t stream, uint64_t *launches, int multi_query) {
   const uint32_t esize = dtype == OI_DTYPE_F32 ? 4u : 2u;
   OiScanParams p;
   p.mat = reinterpret_cast<const uint4 *>(d_mat);
@@ -786,16 +995,30 @@ cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_
   p.doc_base = doc_base;
   p.k = k;
   if (multi_query && nq >= 2 && p.nv <= 96) {
-    // groups of kMultiQ queries share one pass over the matrix (cosine_scan_multi_kernel)
-    uint32_t grid = (uint32_t)num_sms * 2u;
-    const uint32_t max_useful = (uint32_t)((n_rows + 63) / 64);
-    if (grid > max_useful) grid = max_useful ? max_useful : 1;
-    if (grid > ws.max_grid) grid = ws.max_grid;
-    uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
-    rpc = (rpc + 31u) & ~31u;
-    p.rows_per_cta = rpc;
-    grid = (uint32_t)((n_rows + rpc - 1) / rpc);
-    if (grid == 0) grid = 1;
+    // groups of kMultiQ queries share one pass over the matrix
+    uint32_t tile_rows = 0, n_stages = 0;
+    size_t smem = 0;
+    // the pipeline kernel has 96 registers per thread: the group's queries must fit in 48 of them
+    const uint32_t q_regs = (uint32_t)kMultiQ * ((p.nv + 31) / 32) * (dtype == OI_DTYPE_F32 ? 4u : 8u);
+    const bool bulk_multi = multi_query == 2 && q_regs <= 48 && bulk_multi_shape(p.nv * 16u, &tile_rows, &n_stages, &smem);
+    uint32_t grid;
+    if (bulk_multi) {  // cosine_scan_bulk_multi_kernel: one CTA per SM pulling tiles from a counter
+      const uint32_t n_tiles = (uint32_t)((n_rows + tile_rows - 1) / tile_rows);
+      grid = (uint32_t)num_sms;
+      if (grid > n_tiles) grid = n_tiles ? n_tiles : 1;
+      if (grid > ws.max_grid) grid = ws.max_grid;
+      p.rows_per_cta = 0;
+    } else {           // cosine_scan_multi_kernel: two CTAs per SM, contiguous row ranges
+      grid = (uint32_t)num_sms * 2u;
+      const uint32_t max_useful = (uint32_t)((n_rows + 63) / 64);
+      if (grid > max_useful) grid = max_useful ? max_useful : 1;
+      if (grid > ws.max_grid) grid = ws.max_grid;
+      uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
+      rpc = (rpc + 31u) & ~31u;
+      p.rows_per_cta = rpc;
+      grid = (uint32_t)((n_rows + rpc - 1) / rpc);
+      if (grid == 0) grid = 1;
+    }
     p.cand_stride = ws.max_grid * ws.k_stride;
     for (uint32_t g0 = 0; g0 < nq; g0 += kMultiQ) {
       p.nq = nq - g0 < (uint32_t)kMultiQ ? nq - g0 : (uint32_t)kMultiQ;
@@ -805,7 +1028,10 @@ cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_
       p.ticket = ws.ticket + g0;
       p.tile_ctr = ws.tile_ctr + g0;
       p.out_keys = d_out_keys + (size_t)g0 * k;
-      cudaError_t e = dtype == OI_DTYPE_F32 ? launch_multi<float>(p, grid, stream) : launch_multi<__nv_bfloat16>(p, grid, stream);
+      cudaError_t e;
+      if (bulk_multi) e = dtype == OI_DTYPE_F32 ? launch_bulk_multi<float>(p, grid, tile_rows, n_stages, smem, stream)
+                                                : launch_bulk_multi<__nv_bfloat16>(p, grid, tile_rows, n_stages, smem, stream);
+      else e = dtype == OI_DTYPE_F32 ? launch_multi<float>(p, grid, stream) : launch_multi<__nv_bfloat16>(p, grid, stream);
       if (e != cudaSuccess) return e;
       if (launches) ++*launches;
     }

@@ -20,7 +20,8 @@ struct oi_index {
   void *d_emb = nullptr;
   uint64_t emb_rows_loaded = 0;
   int cosine_variant = 1;  // 0 = direct loads, 1 = bulk-copy pipeline with dynamic tiles
-  int cosine_multi_query = 1;  // 1 = calls with several queries scan the matrix once per group of 4 (rows <= 1536 B)
+  int cosine_multi_query = 2;  // calls with several queries scan the matrix once per group of 4 (rows <= 1536 B): 2 = on the
+                               // bulk-copy pipeline where the group fits the registers (f32), 1 = direct loads, 0 = off
 
   // per-call workspaces (device)
   OiCosineWorkspace cws;

@@ -47,7 +47,7 @@ struct OiCosineWorkspace {
 cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_rows, uint32_t dim,
                                   uint32_t doc_base, const float *d_queries, uint32_t nq, uint32_t k,
                                   const OiCosineWorkspace &ws, u64 *d_out_keys, int variant, int num_sms,
-                                  cudaStream_t stream, uint64_t *launches, bool multi_query = false);
+                                  cudaStream_t stream, uint64_t *launches, int multi_query = 0);
 uint32_t oi_cosine_scan_max_grid(int num_sms);
 void oi_cosine_scan_tuning(int tile_rows, int stages);  // experiments: 0 = default shape
 

@@ -63,10 +63,11 @@ def test_cosine_bf16_parity(oi, variant, n, dim, k):
         assert np.max(np.abs(sc[j] - ws)) < 1e-5
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("n,dim,bf16,k,nq", [(50000, 384, False, 100, 9), (30011, 256, False, 10, 4), (4097, 64, False, 1, 2),
                                              (70000, 128, False, 1000, 5), (40000, 768, True, 100, 3), (9000, 128, True, 7, 6),
                                              (3, 64, False, 5, 7)])
-def test_cosine_multi_query_scan_parity(oi, n, dim, bf16, k, nq):
+def test_cosine_multi_query_scan_parity(oi, mode, n, dim, bf16, k, nq):
     """calls with several queries share one matrix pass per group of 4 (rows of at most 1536 bytes): every query's
     list must match the oracle and the single-query kernel; the last group may be partial, shards may be ragged"""
     rows = O.synth_rows_bf16(n, dim) if bf16 else O.synth_rows_f32(n, dim)
@@ -76,6 +77,7 @@ def test_cosine_multi_query_scan_parity(oi, n, dim, bf16, k, nq):
     with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16 if bf16 else oi.DTYPE_F32, max_k=k, max_batch=nq, doc_base=5) as ix:
         ix.load_embeddings(rows)
         ix.set_option("cosine_gemm_min_batch", 0)  # bf16 batches would otherwise take the tensor-core path
+        ix.set_option("cosine_multi_query", mode)  # 1 = direct loads, 2 = bulk-copy pipeline (f32 rows)
         l0 = ix.launch_count()
         ids, sc = ix.search_cosine(qs, k)
         multi_launches = ix.launch_count() - l0

@@ -32,7 +32,7 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
-    for multi in (1, 0):
+    for multi in (2, 1, 0):
         ix.set_option("cosine_multi_query", multi)
         for nb in (4, 16, 64):
             ms = t(nb)
