@@ -470,6 +470,8 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
         }
         tsc = __uint_as_float(gm[k - 1]);
         __syncwarp();
+        // the scratch was written through the generic proxy; the next block's bulk copies write it through the async one
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       // one pass reads and tests the block, 4 x 128 bits per lane per step (the next block's first pass overwrites
       // or clears acc[]).  In steady state only a handful of scores survive the threshold; a group with a survivor

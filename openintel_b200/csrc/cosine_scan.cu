@@ -285,6 +285,38 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_ldg_kernel(co
 // the per-query epilogue (publish, last-CTA merge) is the single-query one.  The bytes stay the bound: per row
 // 3 loads, 48 FMAs and ~5 shuffles per lane at dim 384, ~20 issue cycles per row and SM against ~50 of HBM time.
 // =================================================================================================
+// Warp reduction of 8 values at once: the first three butterfly steps halve the number of live values (a lane
+// keeps the half selected by its bit 4, 3, 2 and sends the other), the last two finish the one that is left:
+// 4 + 2 + 1 + 1 + 1 = 9 shuffles instead of 8 x 5.  On return lanes 4i .. 4i+3 hold the full sum of value i.
+__device__ __forceinline__ float multi_reduce8(const float (&v8)[8], int lane) {
+  float v4[4], v2[2];
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = hi ? v8[j] : v8[j + 4], keep = hi ? v8[j + 4] : v8[j];
+      v4[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = hi ? v4[j] : v4[j + 2], keep = hi ? v4[j + 2] : v4[j];
+      v2[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
+    }
+  }
+  float v1;
+  {
+    const bool hi = lane & 4;
+    const float send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
+    v1 = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+  }
+  v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 2);
+  v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 1);
+  return v1;
+}
+
 constexpr int kMultiQ = 4;
 
 template <typename T, int NVL>
@@ -367,31 +399,7 @@ __global__ void __launch_bounds__(kConsumerThreads, 2) cosine_scan_multi_kernel(
           for (int j = 0; j < NVL; ++j) a = Elem<T>::dot(d[i][j], q[g][j], a);
           v8[g * ROWS + i] = a;
         }
-      float v4[4], v2[2];
-      {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float send = hi ? v8[j] : v8[j + 4], keep = hi ? v8[j + 4] : v8[j];
-          v4[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
-        }
-      }
-      {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float send = hi ? v4[j] : v4[j + 2], keep = hi ? v4[j + 2] : v4[j];
-          v2[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
-        }
-      }
-      float v1;
-      {
-        const bool hi = lane & 4;
-        const float send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
-        v1 = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
-      }
-      v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 2);
-      v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 1);
+      const float v1 = multi_reduce8(v8, lane);
       if ((lane & 3) == 0 && r0 + my_i < stop) {
         const u64 key = oi_make_key(v1, p.doc_base + r0 + my_i);
         if (key > my_thr) oi_sel_push(S[my_g].buf, &S[my_g].cnt, key);
@@ -770,31 +778,7 @@ __global__ void __launch_bounds__(kBMBlock, 1)
             for (int j = 0; j < NVL; ++j) a = Elem<T>::dot(d[i][j], q[g][j], a);
             v8[g * 2 + i] = a;
           }
-        float v4[4], v2[2];
-        {
-          const bool hi = lane & 16;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float send = hi ? v8[j] : v8[j + 4], keep = hi ? v8[j + 4] : v8[j];
-            v4[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
-          }
-        }
-        {
-          const bool hi = lane & 8;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float send = hi ? v4[j] : v4[j + 2], keep = hi ? v4[j + 2] : v4[j];
-            v2[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
-          }
-        }
-        float v1;
-        {
-          const bool hi = lane & 4;
-          const float send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
-          v1 = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
-        }
-        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 2);
-        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, 1);
+        const float v1 = multi_reduce8(v8, lane);
         if ((lane & 3) == 0 && (my_i == 0 || two)) {
           const u64 key = oi_make_key(v1, p.doc_base + tile_row0 + r + (uint32_t)my_i);
           if (key > my_thr) oi_sel_push(S[my_g].buf, &S[my_g].cnt, key);
