@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(kBMBlock, 1)
   const uint32_t ctrig = min((uint32_t)OI_SEL_CAP / 2, max(2u * p.k, 128u));
   const uint32_t max_tiles = max(1u, (uint32_t)OI_SEL_CAP / tile_rows);
   uint32_t tiles_cap = max(1u, 128u / tile_rows);  // short first super-iterations: early, cheap thresholds
-  uint32_t it = 0;
+  uint32_t s = 0, ph = 0;  // ring position (no division per tile)
   bool done = false;
   while (!done) {
     uint32_t room = OI_SEL_CAP;
@@ -744,19 +744,19 @@ __global__ void __launch_bounds__(kBMBlock, 1)
     const u64 my_thr = (uint32_t)my_g < ng ? max(S[my_g].thr, ld_relaxed_u64(p.gthr + my_g)) : ~0ull;
     oi_bar_sync(1, kBulkThreads);  // (cnt, thr) snapshots are uniform before anybody pushes
     for (uint32_t n = 0; n < tiles_now; ++n) {
-      const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
       oi_mbar_wait(&full[s], ph);
       const uint32_t t = s_tile[s];
-      ++it;
+      const uint32_t s_cur = s;
+      if (++s == n_stages) { s = 0; ph ^= 1u; }
       if (t == kTileEnd) {  // every consumer warp sees the same sentinel; the slot holds no data
         __syncwarp();
-        if (lane == 0) oi_mbar_arrive(&empty[s]);
+        if (lane == 0) oi_mbar_arrive(&empty[s_cur]);
         done = true;
         break;
       }
       const uint32_t tile_row0 = t * tile_rows;
       const uint32_t rows = min(tile_rows, p.n_rows - tile_row0);
-      const unsigned char *tile = s_dyn + (size_t)s * tile_bytes;
+      const unsigned char *tile = s_dyn + (size_t)s_cur * tile_bytes;
       for (uint32_t r = warp * 2; r < rows; r += kBulkWarps * 2) {
         const uint4 *rp0 = reinterpret_cast<const uint4 *>(tile + (size_t)r * row_bytes);
         const bool two = r + 1 < rows;
@@ -785,16 +785,18 @@ __global__ void __launch_bounds__(kBMBlock, 1)
         }
       }
       __syncwarp();
-      if (lane == 0) oi_mbar_arrive(&empty[s]);
+      if (lane == 0) oi_mbar_arrive(&empty[s_cur]);
     }
     oi_bar_sync(1, kBulkThreads);
     if (!done) {
-      for (uint32_t g = 0; g < ng; ++g) {
-        if (S[g].cnt > ctrig) {  // uniform over the consumers: read after the barrier
-          oi_sel_compact(S[g].buf, &S[g].cnt, &S[g].thr, p.k, tid, kBulkThreads, 1);
-          if (tid == 0 && S[g].cnt == p.k) atomicMax(p.gthr + g, S[g].thr);
-        }
+      // warp g cuts query g's buffer to its best k (warp-level sort: the four buffers are compacted at the same
+      // time and without CTA barriers)
+      if ((uint32_t)warp < ng && S[warp].cnt > ctrig) {
+        oi_warp_sel_compact(S[warp].buf, &S[warp].cnt, &S[warp].thr, OI_SEL_CAP, p.k, lane);
+        if (lane == 0 && S[warp].cnt == p.k) atomicMax(p.gthr + warp, S[warp].thr);
       }
+      // the (cnt, thr) snapshot of the next round is taken before that round's barrier: close this one here
+      oi_bar_sync(1, kBulkThreads);
     }
   }
   for (uint32_t g = 0; g < ng; ++g) {

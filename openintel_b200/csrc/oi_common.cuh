@@ -96,6 +96,34 @@ __device__ __forceinline__ void oi_sel_compact(u64 *buf, uint32_t *cnt, u64 *thr
   oi_bar_sync(bar, nthreads);
 }
 
+// One WARP keeps the best k of buf[0..*cnt) (sorted descending) and raises *thr when k are held; no CTA barrier
+// is involved, so several warps can compact different buffers at the same time.  cap = buffer capacity.
+__device__ __forceinline__ void oi_warp_sel_compact(u64 *buf, uint32_t *cnt, u64 *thr, uint32_t cap, uint32_t k, int lane) {
+  const uint32_t c = min(*cnt, cap);
+  const uint32_t n = oi_next_pow2(c);
+  __syncwarp();
+  for (uint32_t i = c + lane; i < n; i += 32) buf[i] = 0ull;
+  __syncwarp();
+  for (uint32_t kk = 2; kk <= n; kk <<= 1) {
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = lane; i < (n >> 1); i += 32) {
+        const uint32_t l = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        const uint32_t r = l | j;
+        const u64 a = buf[l], b = buf[r];
+        const bool desc = (l & kk) == 0;
+        if ((a < b) == desc) { buf[l] = b; buf[r] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    const uint32_t keep = min(c, k);
+    *cnt = keep;
+    if (keep == k && buf[k - 1] > *thr) *thr = buf[k - 1];
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (cp.async.bulk, SASS UBLKCP) wrappers
 // ---------------------------------------------------------------------------------------------
