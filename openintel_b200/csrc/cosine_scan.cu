@@ -1001,6 +1001,7 @@ cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_
       if (grid > ws.max_grid) grid = ws.max_grid;
       uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
       rpc = (rpc + 31u) & ~31u;
+      if (rpc == 0) rpc = 32;  // an empty shard: one CTA that finds no rows
       p.rows_per_cta = rpc;
       grid = (uint32_t)((n_rows + rpc - 1) / rpc);
       if (grid == 0) grid = 1;
@@ -1042,6 +1043,7 @@ cudaError_t oi_launch_cosine_scan(const void *d_mat, uint32_t dtype, uint64_t n_
     if (grid > ws.max_grid) grid = ws.max_grid;
     uint32_t rpc = (uint32_t)((n_rows + grid - 1) / grid);
     rpc = (rpc + 31u) & ~31u;
+    if (rpc == 0) rpc = 32;  // an empty shard: one CTA that finds no rows
     p.rows_per_cta = rpc;
     grid = (uint32_t)((n_rows + rpc - 1) / rpc);
     if (grid == 0) grid = 1;

@@ -160,3 +160,20 @@ def test_full_size_config2_properties(oi, variant):
             row = O.synth_rows_f32(1, dim, first=int(ids[j][i]))
             want = float(O.cosine_scores_f32(row, q[j])[0])
             assert abs(want - sc[j][i]) <= F32_TOL * max(abs(want), 1e-2)
+
+
+def test_empty_shard_returns_padding(oi):
+    """a shard without documents (more ranks than documents) answers every query with padding"""
+    dim, k = 64, 5
+    q = O.synth_rows_f32(5, dim, stream=1)
+    with oi.GpuIndex(n_docs=0, dim=dim, max_k=k, max_batch=5) as ix:
+        ix.load_embeddings(np.zeros((0, dim), np.float32))
+        for nq in (1, 5):
+            ids, sc = ix.search_cosine(q[:nq], k)
+            assert np.all(ids == oi.NO_DOC) and np.all(sc == 0)
+        ix.load_bm25(np.zeros(4, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+        ix.bm25_finalize(avgdl=10.0, n_docs_global=100, global_df=np.array([3, 0, 7], np.uint32))
+        ids, sc = ix.search_bm25([[0, 2], [1]], k)
+        assert np.all(ids == oi.NO_DOC) and np.all(sc == 0)
+        ids, rrf, rc, rb = ix.search_hybrid(q[:2], [[0, 2], [1]], k)
+        assert np.all(ids == oi.NO_DOC) and np.all(rrf == 0) and np.all(rc == 0) and np.all(rb == 0)
