@@ -77,6 +77,26 @@ def bench_bm25(a):
             "postings": int(npost), "postings_touched_per_query": touched,
             "algorithmic_GBps": touched * 8 * qps / 1e9, "index_build_s": build_s, "launches_per_batch": launches / (a.steps + a.warmup),
             "groups_override": a.groups}), flush=True)
+    if a.cpu_queries:
+        # the self-written CPU oracle on the same index (read back from the GPU), one thread, a handful of queries:
+        # a baseline next to the GPU number, not a reference implementation (the reference has none)
+        t0 = time.perf_counter()
+        csr = ix.read_bm25(int(npost))
+        w = O.bm25_weights(csr["term_offsets"], csr["doc_ids"], csr["tfs"], csr["doc_len"], O.bm25_idf(a.docs, df))
+        prep_s = time.perf_counter() - t0
+        for name, uniform in (("zipf", False), ("uniform", True)):
+            qs = O.synth_query_terms(a.cpu_queries, 8, cdf, uniform=uniform)
+            got_ids, got_sc = ix.search_bm25(qs, a.k)
+            t0 = time.perf_counter()
+            same = 0
+            for j in range(a.cpu_queries):
+                sc = O.bm25_score_dense(csr["term_offsets"], csr["doc_ids"], w, qs[j], a.docs)
+                wi, ws, _ = O.topk_f32(sc, a.k, only_positive=True)
+                same += int(np.array_equal(wi, got_ids[j]) and np.array_equal(ws.view(np.uint32), got_sc[j].view(np.uint32)))
+            cpu_s = (time.perf_counter() - t0) / a.cpu_queries
+            print(json.dumps({"cpu_oracle": "BM25 %s queries, %d docs, 1 thread (self-written oracle; no reference implementation exists)" % (name, a.docs),
+                              "cpu_queries_per_s": 1.0 / cpu_s, "cpu_ms_per_query": cpu_s * 1e3, "queries": a.cpu_queries,
+                              "bit_identical_to_gpu_lists": "%d / %d" % (same, a.cpu_queries), "oracle_weight_prep_s": prep_s}), flush=True)
     ix.close()
 
 
@@ -162,6 +182,7 @@ def main():
     ap.add_argument("--block-docs", type=int, default=0, help="bm25_block_docs tuning option")
     ap.add_argument("--slots", type=int, default=-1, help="bm25_stage_slots tuning option")
     ap.add_argument("--zipf-only", action="store_true")
+    ap.add_argument("--cpu-queries", type=int, default=0, help="bm25: also time this many queries on the CPU oracle (1 thread)")
     ap.add_argument("--debug", type=int, default=0)
     a = ap.parse_args()
     if a.workload == "gemm":
