@@ -1083,9 +1083,9 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   p.n_blocks = (p.n_docs + p.R - 1) / p.R;
   if (p.n_blocks == 0) p.n_blocks = 1;
   const uint32_t groups = (uint32_t)h->num_sms * ng;
-  // super-ranges per query: enough work items (S x nq) for every warp to take ~24, so that the last items to finish
+  // super-ranges per query: enough work items (S x nq) for every warp to take ~16, so that the last items to finish
   // (queries differ a lot in cost: zero to several dense terms) leave the SMs idle for a small part of the launch
-  const uint32_t ipw = h->bm25_items_per_warp > 0 ? (uint32_t)h->bm25_items_per_warp : 24;
+  const uint32_t ipw = h->bm25_items_per_warp > 0 ? (uint32_t)h->bm25_items_per_warp : 16;
   uint32_t S = (ipw * groups + nq - 1) / nq;
   if (S < 1) S = 1;
   if (S > 256) S = 256;  // the per-query merge is one CTA per query: a few hundred sorted lists at most

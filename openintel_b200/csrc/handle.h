@@ -53,7 +53,7 @@ struct oi_index {
   int bm25_warps = 0;         // tuning: warps per CTA (0 = default)
   int bm25_block_docs = 0;    // tuning: documents per block, a power of two >= 1024 (0 = default)
   int bm25_dense_div = 0;     // tuning (before finalize): a term in >= n_docs / div documents gets a dense column (0 = default 16)
-  int bm25_items_per_warp = 0; // tuning: work items per warp the super-range count aims for (0 = default 24)
+  int bm25_items_per_warp = 0; // tuning: work items per warp the super-range count aims for (0 = default 16)
   int bm25_no_cold_bound = 0;  // tests: disable the cold-start bound (group maxima) of the selection pass
   int bm25_stage_slots = -1;  // tuning: staged 64-posting chunks per warp (-1 = default, 0 = none)
 
