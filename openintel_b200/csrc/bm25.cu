@@ -742,7 +742,7 @@ void oi_bm25_free(oi_index *h) {
   h->bm25 = nullptr;
 }
 
-// capacity of the per-item list workspace in KEYS: the default schedule at k <= 128 (24 items per warp, up to 24 warps
+// capacity of the per-item list workspace in KEYS: a generous schedule at k <= 128 (24 items per warp, up to 24 warps
 // per CTA) or two lists per query at max_k, whichever is larger; a call that would need more lowers its item count
 static size_t bm25_lists_cap(const oi_index *h) {
   const size_t a = (size_t)24 * h->num_sms * 24 * 128, b = 2 * (size_t)h->desc.max_batch * h->desc.max_k;
