@@ -206,6 +206,123 @@ class StoreIndex:
         self.close()
 
 
+# ---- document-sharded lift (one process per GPU, SPEC §5) ----------------------------------------
+def lift_shard(conn, dist, rank=None, world=None, device="cpu"):
+    """This rank's share of a document-sharded index, lifted out of the store every rank can read:
+
+      * the rank tokenises ONLY its contiguous doc range (sharding.shard_range),
+      * the vocabularies are unioned over the ranks (all_gather_object) so term ids are GLOBAL: the sorted union,
+        i.e. exactly the ids the unsharded lift assigns,
+      * the shard's CSR is re-indexed to the global vocabulary (absent terms = empty lists, doc ids shard-local),
+      * df / doc-length sums are all-reduced (sharding.global_bm25_stats), so every shard scores with global
+        N, avgdl and idf.
+
+    `dist` = torch.distributed (initialised, gloo or nccl) or None.  -> dict(doc_base, n_local, n_docs_global, vocab,
+    csr (global vocabulary), global_df, avgdl, post_ids (this shard's))"""
+    from . import sharding
+    n_total = conn.execute("SELECT COUNT(*) FROM posts").fetchone()[0]
+    if dist is not None and dist.get_world_size() > 1:
+        rank, world = dist.get_rank(), dist.get_world_size()
+    else:
+        dist, rank, world = None, 0, 1
+    base, n_local = sharding.shard_range(n_total, world, rank)
+    b = hostlib.IndexBuilder()
+    ids = []
+    cur = conn.execute("SELECT doc_id, id, text FROM posts WHERE doc_id >= ? AND doc_id < ? ORDER BY doc_id", (base, base + n_local))
+    expect = base
+    while True:
+        rows = cur.fetchmany(4096)
+        if not rows:
+            break
+        for doc_id, _, _ in rows:
+            if doc_id != expect:
+                raise ValueError("posts.doc_id must be dense 0..N-1 (gap at %d)" % expect)
+            expect += 1
+        ids.extend(r[1] for r in rows)
+        b.add([r[2] for r in rows])
+    if expect != base + n_local:
+        raise ValueError("posts.doc_id must be dense 0..N-1 (gap at %d)" % expect)
+    local = b.finish()
+    local_vocab = [b.term(i) for i in range(local["n_terms"])]
+    b.close()
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local_vocab)
+        vocab = sorted(set().union(*gathered))
+    else:
+        vocab = local_vocab
+    # local term id -> global term id (both lists are sorted, so the map is increasing)
+    pos = {w: i for i, w in enumerate(vocab)}
+    gid = np.array([pos[w] for w in local_vocab], dtype=np.int64)
+    lens = np.zeros(len(vocab), dtype=np.uint64)
+    if len(gid):
+        lens[gid] = np.diff(local["term_offsets"])
+    off = np.zeros(len(vocab) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    csr = dict(term_offsets=off, doc_ids=local["doc_ids"], tfs=local["tfs"], doc_len=local["doc_len"],
+               n_docs=n_local, n_terms=len(vocab))  # postings keep their order: lists are concatenated by term id
+    gdf, avgdl, n = sharding.global_bm25_stats(dist, lens.astype(np.uint32), int(local["doc_len"].sum()), n_local, device=device)
+    if n != n_total:
+        raise ValueError("the ranks see %d posts in total, the store holds %d" % (n, n_total))
+    return dict(doc_base=base, n_local=n_local, n_docs_global=n_total, vocab=vocab, csr=csr, global_df=gdf, avgdl=float(avgdl),
+                post_ids=ids)
+
+
+class ShardedStoreIndex:
+    """StoreIndex over the GPUs of one box: every rank lifts its doc range (lift_shard), loads it into its GPU with
+    GLOBAL BM25 statistics and joins the NCCL communicator; search() returns the same global lists on every rank."""
+
+    def __init__(self, conn, dist, device_index=0, max_k=100, max_batch=16, k1=1.2, b=0.75):
+        from . import sharding
+        self.dist = dist if (dist is not None and dist.get_world_size() > 1) else None
+        dev = "cuda:%d" % device_index
+        sh = lift_shard(conn, self.dist, device=dev if self.dist else "cpu")
+        self.vocab, self.doc_base, self.n_local, self.n_docs = sh["vocab"], sh["doc_base"], sh["n_local"], sh["n_docs_global"]
+        self.term_id = {w: i for i, w in enumerate(self.vocab)}
+        self.dim = store_dim(conn)
+        if self.dim is None:
+            raise ValueError("store has no embeddings")
+        rows = np.empty((self.n_local, self.dim), dtype=np.float32)
+        cur = conn.execute("SELECT doc_id, vec FROM embeddings WHERE doc_id >= ? AND doc_id < ? ORDER BY doc_id",
+                           (self.doc_base, self.doc_base + self.n_local))
+        got = 0
+        for doc_id, blob in cur:
+            if doc_id != self.doc_base + got:
+                raise ValueError("embedding missing for doc %d" % (self.doc_base + got))
+            rows[got] = np.frombuffer(blob, dtype="<f4")
+            got += 1
+        if got != self.n_local:
+            raise ValueError("embedding missing for doc %d" % (self.doc_base + got))
+        rows = normalise_rows_f32(rows)
+        self.ix = capi.GpuIndex(n_docs=self.n_local, dim=self.dim, device=device_index, doc_base=self.doc_base, max_k=max_k, max_batch=max_batch)
+        try:
+            self.ix.load_embeddings(rows)
+            c = sh["csr"]
+            self.ix.load_bm25(c["term_offsets"], c["doc_ids"], c["tfs"], c["doc_len"])
+            self.ix.bm25_finalize(k1=k1, b=b, avgdl=sh["avgdl"], n_docs_global=self.n_docs, global_df=sh["global_df"])
+            if self.dist:
+                self.ix.comm_init(self.dist.get_rank(), self.dist.get_world_size(), sharding.broadcast_unique_id(self.dist, device=dev))
+        except Exception:
+            self.ix.close()
+            raise
+
+    def query_terms(self, texts):
+        return [np.array([self.term_id[t] for t in hostlib.tokenize(x) if t in self.term_id], dtype=np.uint32) for x in texts]
+
+    def search(self, texts, vectors, k, rrf_k=60):
+        q = normalise_rows_f32(np.asarray(vectors, dtype=np.float32).reshape(len(texts), self.dim))
+        return self.ix.search_hybrid(q, self.query_terms(texts), k, rrf_k)
+
+    def close(self):
+        self.ix.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 # ---- synthetic posts of BASELINE.json configs[0] ------------------------------------------------
 def synth_posts(n_docs, vocab, seed, oracle_mod):
     """10k-post style synthetic corpus: token ids from the SPEC §9 Zipf generator,

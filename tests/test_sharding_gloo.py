@@ -104,3 +104,71 @@ def test_two_gloo_ranks_reproduce_the_unsharded_lists():
             wi, ws, _ = O.topk_f32(c, K)
             assert np.array_equal(out["cos"][0][j], wi)
             assert np.array_equal(out["cos"][1][j].view(np.uint32), ws.view(np.uint32))
+
+
+# ---- document-sharded lift out of the SQLite post store (openintel_b200.store.lift_shard) ----------------------
+N_POSTS = 1501
+
+
+def _store_worker(rank, world, port, path, q):
+    import torch.distributed as dist
+    from openintel_b200 import store
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        conn = store.open_store(path)
+        sh = store.lift_shard(conn, dist)
+        conn.close()
+        q.put((rank, sh))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_store_lift_equals_the_unsharded_lift(tmp_path, world):
+    """every rank tokenises only its doc range; the union vocabulary, the re-indexed shard CSRs and the all-reduced
+    statistics must add up to exactly the unsharded lift (global term ids, global df / avgdl / N)"""
+    import runpy
+    import torch.multiprocessing as mp
+    from openintel_b200 import hostlib, store
+    runpy.run_path(os.path.join(os.path.dirname(hostlib.__file__), "host", "build.py"), run_name="__build__")
+    path = str(tmp_path / "posts.db")
+    posts, _ = store.synth_posts(N_POSTS, 700, O.SEED, O)
+    conn = store.open_store(path, dim=8)
+    store.insert_posts(conn, posts, np.ones((N_POSTS, 8), np.float32))
+    b, whole, ids = store.lift_csr(conn)
+    vocab = [b.term(i) for i in range(whole["n_terms"])]
+    conn.close()
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_store_worker, args=(r, world, port, path, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+
+    df = np.diff(whole["term_offsets"]).astype(np.uint32)
+    avgdl = float(np.float32(np.float64(whole["doc_len"].sum()) / N_POSTS))
+    lists = [[] for _ in vocab]
+    tfs = [[] for _ in vocab]
+    all_ids, all_dl = [], []
+    for rank, sh in res:
+        assert (sh["doc_base"], sh["n_local"]) == sharding.shard_range(N_POSTS, world, rank)
+        assert sh["vocab"] == vocab and sh["n_docs_global"] == N_POSTS
+        assert np.array_equal(sh["global_df"], df) and sh["avgdl"] == avgdl
+        c = sh["csr"]
+        assert c["n_terms"] == len(vocab) and c["n_docs"] == sh["n_local"] and len(c["doc_len"]) == sh["n_local"]
+        off = c["term_offsets"].astype(np.int64)
+        for t in range(len(vocab)):
+            lists[t].extend((c["doc_ids"][off[t]:off[t + 1]].astype(np.int64) + sh["doc_base"]).tolist())
+            tfs[t].extend(c["tfs"][off[t]:off[t + 1]].tolist())
+        all_ids.extend(sh["post_ids"])
+        all_dl.extend(c["doc_len"].tolist())
+    w_off = whole["term_offsets"].astype(np.int64)
+    for t in range(len(vocab)):
+        assert lists[t] == whole["doc_ids"][w_off[t]:w_off[t + 1]].tolist(), vocab[t]
+        assert tfs[t] == whole["tfs"][w_off[t]:w_off[t + 1]].tolist()
+    assert all_ids == ids and all_dl == whole["doc_len"].tolist()
