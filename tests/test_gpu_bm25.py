@@ -316,3 +316,44 @@ def test_full_size_config3_properties(oi):
         m = len(order)
         assert np.array_equal(cat_ids[order], ids[j][:m]) and np.array_equal(cat_sc[order].view(np.uint32), sc[j][:m].view(np.uint32))
         assert np.all(ids[j][m:] == oi.NO_DOC)
+
+
+def test_gpu_matches_the_published_formulas_on_hand_sized_input(oi):
+    """the GPU path against the published definitions directly (50-digit decimals / exact fractions from
+    tests/test_oracle_known_answers.py), without the oracle in between: Lucene-idf BM25, RRF with k = 60"""
+    from decimal import Decimal
+    from fractions import Fraction
+    from test_oracle_known_answers import _bm25_decimal, _csr
+    docs = [[0, 1, 1, 2], [0, 2, 2, 2, 3, 4, 4], [0, 1, 5], [0, 0, 0, 3], [0, 4, 5, 5, 5, 5, 1, 2, 3], [0, 3]]
+    vocab, k = 7, 4
+    off, di, tf, dl = _csr(docs, vocab)
+    rows = np.zeros((6, 64), dtype=np.float32)
+    for d in range(6):
+        rows[d, d] = 1.0  # orthonormal rows: cosine scores are exactly 0 or the query component
+    q = np.zeros((1, 64), dtype=np.float32)
+    q[0, :6] = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6]
+    q /= np.linalg.norm(q)
+    with oi.GpuIndex(n_docs=6, dim=64, max_k=k, max_batch=1) as ix:
+        ix.load_embeddings(rows)
+        ix.load_bm25(off, di, tf, dl)
+        ix.bm25_finalize()
+        for query in ([1, 2], [0], [5, 5, 3], [4, 6, 9], [0, 1, 2, 3, 4, 5]):
+            ids, sc = ix.search_bm25([query], k)
+            want = _bm25_decimal(docs, vocab, query)
+            exact = sorted([(-x, d) for d, x in enumerate(want) if x > 0])[:k]
+            assert [int(i) for i in ids[0][:len(exact)]] == [d for _, d in exact], query
+            for i, s in zip(ids[0][:len(exact)], sc[0]):
+                assert abs(Decimal(float(s)) - want[int(i)]) <= Decimal("2e-6") * max(want[int(i)], Decimal(1))
+            assert np.all(ids[0][len(exact):] == oi.NO_DOC)
+        cos_ids, cos_sc = ix.search_cosine(q, k)
+        assert [int(i) for i in cos_ids[0]] == [5, 4, 3, 2] and np.allclose(cos_sc[0], q[0, [5, 4, 3, 2]], atol=1e-7)
+        h_ids, h_rrf, h_rc, h_rb = ix.search_hybrid(q, [[5, 5, 3]], k)
+        bm_ids, _ = ix.search_bm25([[5, 5, 3]], k)
+        fused = {}
+        for lst in ([int(i) for i in cos_ids[0]], [int(i) for i in bm_ids[0] if i != oi.NO_DOC]):
+            for r, d in enumerate(lst, 1):
+                fused[d] = fused.get(d, Fraction(0)) + Fraction(1, 60 + r)
+        order = sorted(fused, key=lambda d: (-fused[d], d))[:k]
+        assert [int(i) for i in h_ids[0][:len(order)]] == order
+        for d, v in zip(h_ids[0][:len(order)], h_rrf[0]):
+            assert abs(Fraction(float(v)) - fused[int(d)]) < Fraction(1, 10 ** 8)
