@@ -119,6 +119,12 @@ def normalise_rows_f32(rows):
     return rows / n[:, None]
 
 
+def to_bf16_rne(rows):
+    """f32 -> bf16 bit patterns (uint16), round to nearest even (SPEC §2 bf16 path); finite inputs"""
+    u = np.ascontiguousarray(rows, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) >> np.uint32(16)).astype(np.uint16)
+
+
 def lift_csr(conn, chunk=4096):
     """Tokenises every post with the reference tokenizer and builds vocabulary + CSR on the host.
     -> (IndexBuilder, csr dict, post ids in doc order)"""
@@ -174,9 +180,8 @@ class StoreIndex:
         rows = lift_embeddings(conn, self.n_docs, self.dim)
         self.ix = capi.GpuIndex(n_docs=self.n_docs, dim=self.dim, dtype=dtype, device=device, max_k=max_k, max_batch=max_batch)
         try:
-            if dtype == capi.DTYPE_BF16:
-                raise NotImplementedError("store -> bf16 index: convert rows with round-to-nearest-even before load")
-            self.ix.load_embeddings(rows)
+            # a bf16 index stores the normalised rows rounded to nearest even (SPEC §2)
+            self.ix.load_embeddings(to_bf16_rne(rows) if dtype == capi.DTYPE_BF16 else rows)
             self.ix.load_bm25(csr["term_offsets"], csr["doc_ids"], csr["tfs"], csr["doc_len"])
             self.ix.bm25_finalize(k1=k1, b=b)
         except Exception:

@@ -128,3 +128,25 @@ def test_cpp_host_layer_lifts_the_store_and_searches(oi, tmp_path):
     r = subprocess.run([demo, "--store", str(tmp_path / "nope.db"), str(tmp_path / "queries.txt"), str(tmp_path / "qemb.f32"), str(k)],
                        capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "post-store" in r.stderr
+
+
+def test_store_bf16_index(oi, tmp_path):
+    """a bf16 index lifted from the store: rows normalised in f32, rounded to nearest even, scanned on the bf16 path"""
+    from openintel_b200 import store
+    n, vocab, dim, k = 6000, 800, 128, 10
+    posts, _ = store.synth_posts(n, vocab, O.SEED, O)
+    emb = O.synth_rows_f32(n, dim) * np.float32(0.5)
+    conn = store.open_store(str(tmp_path / "p.db"), dim=dim)
+    store.insert_posts(conn, posts, emb)
+    texts = [" ".join(posts[3]["text"].split()[:5])]
+    qv = O.synth_planted_queries(1, dim, n)[0]
+    with store.StoreIndex(conn, dtype=oi.DTYPE_BF16, max_k=k, max_batch=2) as sx:
+        got = sx.search(texts, qv, k)[0]
+        cos_ids, cos_sc = sx.ix.search_cosine(store.normalise_rows_f32(qv), k)
+    conn.close()
+    rows16 = O.f32_to_bf16(store.normalise_rows_f32(emb))
+    allsc = O.cosine_scores_bf16(rows16, store.normalise_rows_f32(qv)[0])
+    wi, ws, _ = O.topk_f64(allsc, k)
+    assert_ranked_close(cos_ids[0], cos_sc[0], wi, ws, allsc, 2e-3)
+    assert len(got) == k and len({h["doc_id"] for h in got}) == k
+    assert {h["doc_id"] for h in got if h["rank_cosine"]} <= set(int(i) for i in cos_ids[0])

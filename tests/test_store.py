@@ -130,3 +130,11 @@ def test_cpp_store_reader_lifts_the_same_index(tmp_path):
     cs.close()
     with pytest.raises(OSError):
         hostlib.CppPostStore(str(tmp_path / "missing.db"))
+
+
+def test_bf16_rounding_is_nearest_even():
+    x = np.random.RandomState(2).randn(500, 32).astype(np.float32)
+    x[0, :4] = np.array([0x3F808000, 0x3F818000, 0x3F80FFFF, 0x3F807FFF], dtype=np.uint32).view(np.float32)  # ties and neighbours
+    got = store.to_bf16_rne(x)
+    assert got.dtype == np.uint16 and np.array_equal(got, O.f32_to_bf16(x))
+    assert [hex(v) for v in got[0, :4]] == ["0x3f80", "0x3f82", "0x3f81", "0x3f80"]
