@@ -326,27 +326,3 @@ class ShardedStoreIndex:
 
     def __exit__(self, *a):
         self.close()
-
-
-# ---- synthetic posts of BASELINE.json configs[0] ------------------------------------------------
-def synth_posts(n_docs, vocab, seed, oracle_mod):
-    """10k-post style synthetic corpus: token ids from the SPEC §9 Zipf generator,
-    rendered as words ("w<id>", with a few upper-case / punctuation variants so the tokenizer has work to do).
-    `oracle_mod` supplies the generator (tests / tools pass the `oracle` package); the product never imports it."""
-    O = oracle_mod
-    cdf = O.zipf_cdf(vocab)
-    dl = O.synth_doc_lens(n_docs, seed)
-    off, toks = O.synth_tokens(dl, cdf, seed)
-    posts = []
-    for d in range(n_docs):
-        words = []
-        for j, t in enumerate(toks[int(off[d]):int(off[d + 1])]):
-            w = "w%d" % t
-            if (d + j) % 7 == 0:
-                w = w.upper()
-            if (d + j) % 5 == 0:
-                w = "$" + w + ","
-            words.append(w)
-        posts.append(dict(id="post-%d" % d, source=SOURCES[d % 2], author="user%d" % (d % 97), text=" ".join(words),
-                          created_at="2026-10-18T00:00:%02dZ" % (d % 60), engagement=d % 1000))
-    return posts, cdf

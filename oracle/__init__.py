@@ -288,3 +288,26 @@ def alignment(has_market, total, net, pct_change, min_sample=10, net_thr=0.05, p
     return ALIGNMENT[lib().oio_alignment(i32(int(has_market)), u64(total), C.c_double(net),
                                          C.c_double(pct_change), u64(min_sample), C.c_double(net_thr),
                                          C.c_double(price_thr))]
+
+
+# ---- synthetic posts of BASELINE.json configs[0] (test / tool input, not product code) -----------
+def synth_posts(n_docs, vocab, seed=SEED):
+    """10k-post style synthetic corpus: token ids from the SPEC §9 Zipf generator,
+    rendered as words ("w<id>", with a few upper-case / punctuation variants so the tokenizer has work to do) in
+    dicts that carry the reference's SocialPost fields.  -> (posts, zipf cdf)"""
+    cdf = zipf_cdf(vocab)
+    dl = synth_doc_lens(n_docs, seed)
+    off, toks = synth_tokens(dl, cdf, seed)
+    posts = []
+    for d in range(n_docs):
+        words = []
+        for j, t in enumerate(toks[int(off[d]):int(off[d + 1])]):
+            w = "w%d" % t
+            if (d + j) % 7 == 0:
+                w = w.upper()
+            if (d + j) % 5 == 0:
+                w = "$" + w + ","
+            words.append(w)
+        posts.append(dict(id="post-%d" % d, source=("reddit", "bluesky")[d % 2], author="user%d" % (d % 97), text=" ".join(words),
+                          created_at="2026-10-18T00:00:%02dZ" % (d % 60), engagement=d % 1000))
+    return posts, cdf

@@ -45,7 +45,7 @@ def _python_csr(texts):
 @pytest.mark.parametrize("n,vocab,dim,k", [(10000, 50000, 384, 10), (3000, 500, 64, 100)])
 def test_store_hybrid_matches_oracle(oi, tmp_path, n, vocab, dim, k):
     from openintel_b200 import store
-    posts, _ = store.synth_posts(n, vocab, O.SEED, O)
+    posts, _ = O.synth_posts(n, vocab, O.SEED)
     emb = O.synth_rows_f32(n, dim) * np.float32(3.5)  # un-normalised in the store: the lift normalises
     conn = store.open_store(str(tmp_path / "posts.db"), dim=dim)
     store.insert_posts(conn, posts, emb)
@@ -96,7 +96,7 @@ def test_cpp_host_layer_lifts_the_store_and_searches(oi, tmp_path):
     import subprocess
     from openintel_b200 import hostlib, store
     n, vocab, dim, k = 4000, 3000, 96, 10
-    posts, _ = store.synth_posts(n, vocab, O.SEED, O)
+    posts, _ = O.synth_posts(n, vocab, O.SEED)
     emb = O.synth_rows_f32(n, dim) * np.float32(2.0)
     path = str(tmp_path / "posts.db")
     conn = store.open_store(path, dim=dim)
@@ -134,7 +134,7 @@ def test_store_bf16_index(oi, tmp_path):
     """a bf16 index lifted from the store: rows normalised in f32, rounded to nearest even, scanned on the bf16 path"""
     from openintel_b200 import store
     n, vocab, dim, k = 6000, 800, 128, 10
-    posts, _ = store.synth_posts(n, vocab, O.SEED, O)
+    posts, _ = O.synth_posts(n, vocab, O.SEED)
     emb = O.synth_rows_f32(n, dim) * np.float32(0.5)
     conn = store.open_store(str(tmp_path / "p.db"), dim=dim)
     store.insert_posts(conn, posts, emb)

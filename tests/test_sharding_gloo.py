@@ -134,7 +134,7 @@ def test_sharded_store_lift_equals_the_unsharded_lift(tmp_path, world):
     from openintel_b200 import hostlib, store
     runpy.run_path(os.path.join(os.path.dirname(hostlib.__file__), "host", "build.py"), run_name="__build__")
     path = str(tmp_path / "posts.db")
-    posts, _ = store.synth_posts(N_POSTS, 700, O.SEED, O)
+    posts, _ = O.synth_posts(N_POSTS, 700, O.SEED)
     conn = store.open_store(path, dim=8)
     store.insert_posts(conn, posts, np.ones((N_POSTS, 8), np.float32))
     b, whole, ids = store.lift_csr(conn)

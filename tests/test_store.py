@@ -33,7 +33,7 @@ def test_post_text_rules_match_reference_tests():
 
 
 def _posts(n, vocab=400):
-    return store.synth_posts(n, vocab, O.SEED, O)[0]
+    return O.synth_posts(n, vocab, O.SEED)[0]
 
 
 def _python_csr(texts):

@@ -25,7 +25,7 @@ def main():
     a = ap.parse_args()
     import oracle as O
     from openintel_b200 import store
-    posts, _ = store.synth_posts(a.docs, a.vocab, O.SEED, O)
+    posts, _ = O.synth_posts(a.docs, a.vocab, O.SEED)
     emb = O.synth_rows_f32(a.docs, a.dim)
     conn = store.open_store(":memory:", dim=a.dim)
     t0 = time.perf_counter()

@@ -23,7 +23,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     n, vocab, dim, k = 20001, 5000, 128, 20
     path = os.path.join(tempfile.gettempdir(), "oi_store_check_%s.db" % os.environ.get("MASTER_PORT", "0"))
-    posts, _ = store.synth_posts(n, vocab, O.SEED, O)
+    posts, _ = O.synth_posts(n, vocab, O.SEED)
     if rank == 0:
         if os.path.exists(path):
             os.remove(path)
