@@ -167,13 +167,38 @@ def _dev_time(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
+def _zipf_cdf(vocab):
+    """cumulative Zipf(s = 1) distribution over term ranks 1..vocab (numpy; inputs of the secondary legs only)"""
+    import numpy as np
+    w = 1.0 / np.arange(1, vocab + 1, dtype=np.float64)
+    c = np.cumsum(w)
+    c /= c[-1]
+    c[-1] = 1.0
+    return c
+
+
+def _zipf_queries(nq, terms, cdf, seed):
+    """nq queries of `terms` DISTINCT term ids drawn from the Zipf distribution (head-heavy, the realistic case)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = np.empty((nq, terms), dtype=np.uint32)
+    for j in range(nq):
+        seen = []
+        while len(seen) < terms:
+            t = int(np.searchsorted(cdf, rng.random(), side="right"))
+            t = min(t, len(cdf) - 1)
+            if t not in seen:
+                seen.append(t)
+        out[j] = seen
+    return out
+
+
 def secondary_workloads(dev):
     """The other single-GPU configurations of BASELINE.json, measured in the same run (device-timed,
     inputs resident in HBM).  Informational: the headline line above stays configs[1]."""
     import numpy as np
     import torch
     import openintel_b200 as oi
-    import oracle as O
     out = {}
     stream = torch.cuda.current_stream().cuda_stream
     # one 10M-document index serves configs[3] (768-dim bf16 rows, batch 256, tcgen05 path), configs[2] (BM25 over a
@@ -194,11 +219,11 @@ def secondary_workloads(dev):
             "queries_per_s": nb / (ms * 1e-3), "ms_per_batch": ms, "tensor_tflops": tf, "hbm_gbs": n * dim * 2 / (ms * 1e-3) / 1e9,
             "frac_of_measured_bf16_sustained": tf / peaks["bf16_tflops_sustained"] if peaks else None,
             "frac_of_measured_bf16_burst": tf / peaks["bf16_tflops"] if peaks else None}
-        cdf = O.zipf_cdf(vocab)
+        cdf = _zipf_cdf(vocab)
         ix.synth_bm25(SEED, vocab, cdf)
         ix.bm25_finalize()
         df, _, npost = ix.bm25_local_stats()
-        pools = [O.synth_query_terms(nbm, 8, cdf, first=p * nbm) for p in range(4)]
+        pools = [_zipf_queries(nbm, 8, cdf, 100 + p) for p in range(4)]
         touched = float(np.mean([df[p].astype(np.int64).sum(axis=1).mean() for p in pools]))
         qt = [torch.from_numpy(p.astype(np.int32).reshape(-1)).to(dev) for p in pools]
         offs = torch.arange(0, nbm * 8 + 1, 8, dtype=torch.int32, device=dev)
@@ -228,7 +253,7 @@ def secondary_workloads(dev):
     # hybrid BM25 + cosine + RRF on the configs[1] corpus (1M x 384 f32, 1M-term Zipf vocabulary), batch 16
     try:
         n, vocab, nb = N_DOCS, 1_000_000, 16
-        cdf = O.zipf_cdf(vocab)
+        cdf = _zipf_cdf(vocab)
         ix = oi.GpuIndex(n_docs=n, dim=DIM, max_k=TOPK, max_batch=nb)
         ix.synth_embeddings(SEED)
         ix.synth_bm25(SEED, vocab, cdf)
@@ -236,7 +261,7 @@ def secondary_workloads(dev):
         g = torch.Generator().manual_seed(7)
         qv = torch.randn(4, nb, DIM, generator=g)
         qv = (qv / qv.norm(dim=2, keepdim=True)).to(dev)
-        qt = [torch.from_numpy(O.synth_query_terms(nb, 8, cdf, first=p * nb).astype(np.int32).reshape(-1)).to(dev) for p in range(4)]
+        qt = [torch.from_numpy(_zipf_queries(nb, 8, cdf, 200 + p).astype(np.int32).reshape(-1)).to(dev) for p in range(4)]
         offs = torch.arange(0, nb * 8 + 1, 8, dtype=torch.int32, device=dev)
         o = [torch.empty(nb, TOPK, dtype=torch.int32, device=dev) for _ in range(3)]
         rrf = torch.empty(nb, TOPK, dtype=torch.float32, device=dev)
