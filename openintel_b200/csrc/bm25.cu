@@ -6,7 +6,7 @@
 //
 // Scoring kernel (bm25_blocked_kernel), the hot path of BASELINE config 3:
 //   * a work item is (query q, super-range s of documents); items are handed out from an atomic
-//     counter, s-major, ~24 per warp, so that the warps running at the same time walk the same part
+//     counter, s-major, ~16 per warp, so that the warps running at the same time walk the same part
 //     of every posting list (the second reader of a posting finds it in L2) and the last items to
 //     finish leave the SMs idle for a small part of the launch.
 //   * one WARP owns an item.  It walks its super-range block by block (R = 2048 documents); the
