@@ -43,9 +43,34 @@ static oi_status create_fail(oi_status code, const std::string &msg) {
 
 extern "C" const char *oi_version(void) { return "openintel_gpu 0.1 (sm_100a; cosine scan + BM25 + RRF; no CPU fallback)"; }
 
+// The message is copied under the handle's lock into a thread-local string: a failing call on another thread may
+// reassign h->err at any time, and the pointer handed out must stay valid until this thread asks again.
 extern "C" const char *oi_last_error(const oi_index *h) {
   if (!h) return g_create_error.c_str();
-  return h->err.c_str();
+  static thread_local std::string t_msg;
+  oi_index *hm = const_cast<oi_index *>(h);
+  std::lock_guard<std::mutex> lock(hm->mu);
+  t_msg = hm->err;
+  return t_msg.c_str();
+}
+
+// Device-side ordering of two calls that share the handle's workspaces but were enqueued on different streams
+// (ADVICE r1): the stream of this call waits for the event recorded at the end of the previous one.  A capturing
+// stream is left alone (the host that captures owns the ordering of its graph).
+static bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+static cudaError_t call_begin(oi_index *h, cudaStream_t st) {
+  if (!h->has_last || st == h->last_stream || stream_is_capturing(st)) return cudaSuccess;
+  return cudaStreamWaitEvent(st, h->ev_last, 0);
+}
+static cudaError_t call_end(oi_index *h, cudaStream_t st) {
+  if (stream_is_capturing(st)) return cudaSuccess;
+  cudaError_t e = cudaEventRecord(h->ev_last, st);
+  if (e == cudaSuccess) { h->has_last = true; h->last_stream = st; }
+  return e;
 }
 
 extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) {
@@ -82,6 +107,10 @@ extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) 
   }
   h->num_sms = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
 
   const size_t emb_bytes = (size_t)desc->n_docs * desc->dim * esize;
   if (emb_bytes && (e = cudaMalloc(&h->d_emb, emb_bytes)) != cudaSuccess) return bail("cudaMalloc(embeddings)", e);
@@ -89,8 +118,8 @@ extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) 
   const size_t B = desc->max_batch, K = desc->max_k;
   h->cws.max_grid = oi_cosine_scan_max_grid(h->num_sms);
   h->cws.k_stride = desc->max_k;
-  // the single-query scan runs one launch per query: candidate slots for min(B, 64) queries
-  // are enough because launches on one stream run back to back and each re-arms its slot
+  // one candidate area per query of a batch: the persistent scan launch walks the batch's queries back to back
+  // and the epilogue of query i overlaps the scan of query i + 1
   h->cws_slots = B;
   if ((e = cudaMalloc(&h->cws.cand, h->cws_slots * h->cws.max_grid * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(cand)", e);
   if ((e = cudaMalloc(&h->cws.gthr, B * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(gthr)", e);
@@ -116,6 +145,8 @@ extern "C" void oi_index_destroy(oi_index *h) {
   if (!h) return;
   cudaSetDevice(h->desc.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
+  if (h->has_last) cudaEventSynchronize(h->ev_last);  // a `_dev` call may still be running on a caller's stream
   oi_comm_destroy(h);
   oi_bm25_free(h);
   oi_gemm_free(h);
@@ -134,6 +165,10 @@ extern "C" void oi_index_destroy(oi_index *h) {
   cudaFree(h->d_pin_out);
   cudaFreeHost(h->h_pin_in);
   cudaFreeHost(h->h_pin_out);
+  if (h->ev_last) cudaEventDestroy(h->ev_last);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -154,8 +189,34 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->cosine_multi_query = (int)value;
     return OI_OK;
   }
-  if (!strcmp(name, "cosine_scan_shape")) {  // experiments: value = tile_rows * 256 + stages (0 = default)
+  if (!strcmp(name, "cosine_scan_shape")) {  // experiments (process-wide): value = tile_rows * 256 + stages (0 = default)
+    // a tile may not hold more rows than half the CTA's candidate buffer, or a cold tile could overflow it
+    OI_REQUIRE(value >= 0 && (value >> 8) <= OI_MAX_K && (value & 255) <= 8, "cosine_scan_shape: tile_rows must be <= 1024 and stages <= 8");
     oi_cosine_scan_tuning((int)(value >> 8), (int)(value & 255));
+    return OI_OK;
+  }
+  if (!strcmp(name, "cosine_gemm_lite")) {  // experiments: the stand-alone cosine call runs the 96 KB-ring kernel too
+    h->gemm_force_lite = value != 0;
+    return OI_OK;
+  }
+  if (!strcmp(name, "hybrid_overlap")) {
+    OI_REQUIRE(value >= 0 && value <= 2, "hybrid_overlap must be 0 (legs back to back), 1 (co-resident lite kernels) or 2 (SM partition)");
+    h->hybrid_overlap = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "overlap_bm25_warps")) {
+    OI_REQUIRE(value >= 1 && value <= 16, "overlap_bm25_warps must be in 1..16");
+    h->overlap_bm25_warps = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "overlap_bm25_slots")) {
+    OI_REQUIRE(value >= 0 && value <= 8, "overlap_bm25_slots must be in 0..8");
+    h->overlap_bm25_slots = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "overlap_gemm_sms")) {
+    OI_REQUIRE(value >= 2 && value < h->num_sms, "overlap_gemm_sms must be in 2..num_sms-1");
+    h->overlap_gemm_sms = (int)value;
     return OI_OK;
   }
   if (!strcmp(name, "cosine_gemm_min_batch")) {
@@ -167,7 +228,8 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->gemm_force_2d = (int)value;
     return OI_OK;
   }
-  if (!strcmp(name, "cosine_gemm_debug")) {
+  if (!strcmp(name, "cosine_gemm_debug")) {  // timing experiments: results are garbage while it is set
+    OI_REQUIRE(value >= 0 && value <= 7, "cosine_gemm_debug is a 3-bit mask");
     h->gemm_debug = (int)value;
     return OI_OK;
   }
@@ -177,7 +239,7 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     return OI_OK;
   }
   if (!strcmp(name, "cosine_gemm_sample_tiles")) {
-    OI_REQUIRE(value >= 0 && value <= 7, "cosine_gemm_sample_tiles must be in 0..7");
+    OI_REQUIRE(value >= 0 && value <= 56, "cosine_gemm_sample_tiles must be in 0..56");
     h->gemm_sample_tiles = (int)value;
     return OI_OK;
   }
@@ -232,11 +294,17 @@ extern "C" oi_status oi_index_load_embeddings(oi_index *h, const void *rows, uin
   OI_REQUIRE(rows != nullptr || n == 0, "rows is NULL");
   OI_REQUIRE(first_doc + n <= h->desc.n_docs, "rows [%llu, %llu) outside the shard (n_docs = %llu)",
              (unsigned long long)first_doc, (unsigned long long)(first_doc + n), (unsigned long long)h->desc.n_docs);
+  // coverage, not a row count: chunks extend the loaded prefix [0, emb_rows_loaded) or rewrite rows inside it, so
+  // "all rows loaded" can never be claimed while part of the matrix is uninitialised HBM
+  if (first_doc > h->emb_rows_loaded)
+    return h->fail(OI_ERR_STATE, "rows [%llu, ...) would leave a gap after the %llu rows loaded so far: load chunks in order",
+                   (unsigned long long)first_doc, (unsigned long long)h->emb_rows_loaded);
   OI_CK(cudaSetDevice(h->desc.device));
   const size_t row_bytes = (size_t)h->desc.dim * h->esize();
+  OI_CK(call_begin(h, h->stream));
   if (n) OI_CK(cudaMemcpyAsync((char *)h->d_emb + first_doc * row_bytes, rows, n * row_bytes, cudaMemcpyHostToDevice, h->stream));
   OI_CK(cudaStreamSynchronize(h->stream));
-  h->emb_rows_loaded += n;
+  if (first_doc + n > h->emb_rows_loaded) h->emb_rows_loaded = first_doc + n;
   return OI_OK;
 }
 
@@ -244,6 +312,7 @@ extern "C" oi_status oi_index_synth_embeddings(oi_index *h, uint64_t seed) {
   if (!h) return OI_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(h->mu);
   OI_CK(cudaSetDevice(h->desc.device));
+  OI_CK(call_begin(h, h->stream));
   OI_CK(oi_launch_synth_embeddings(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, seed, 0, h->desc.doc_base, h->stream, &h->launches));
   OI_CK(cudaStreamSynchronize(h->stream));
   h->emb_rows_loaded = h->desc.n_docs;
@@ -257,6 +326,7 @@ extern "C" oi_status oi_index_read_embeddings(oi_index *h, void *rows, uint64_t 
   OI_REQUIRE(first_doc + n <= h->desc.n_docs, "rows outside the shard");
   OI_CK(cudaSetDevice(h->desc.device));
   const size_t row_bytes = (size_t)h->desc.dim * h->esize();
+  OI_CK(call_begin(h, h->stream));
   if (n) OI_CK(cudaMemcpyAsync(rows, (const char *)h->d_emb + first_doc * row_bytes, n * row_bytes, cudaMemcpyDeviceToHost, h->stream));
   OI_CK(cudaStreamSynchronize(h->stream));
   return OI_OK;
@@ -269,15 +339,21 @@ static oi_status check_search_args(oi_index *h, uint32_t nq, uint32_t k) {
   return OI_OK;
 }
 
+static bool use_gemm(const oi_index *h, uint32_t nq, uint32_t k) {
+  return h->gemm_min_batch > 0 && nq >= (uint32_t)h->gemm_min_batch && oi_gemm_eligible(h, nq, k);
+}
+
 // local scan -> (multi-GPU: all-gather + merge) -> global cosine key lists in d_keys_cos
 // `local_only` (multi-GPU hybrid): leave the shard-local lists there and skip the exchange
-static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, cudaStream_t st, u64 *local_only = nullptr) {
+// gemm_lite / gemm_ctas: the hybrid call's overlap modes (see hybrid_enqueue)
+static oi_status cosine_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, cudaStream_t st, u64 *local_only = nullptr,
+                             bool gemm_lite = false, uint32_t gemm_ctas = 0) {
   if (h->emb_rows_loaded < h->desc.n_docs) return h->fail(OI_ERR_STATE, "embeddings not loaded (%llu of %llu rows)", (unsigned long long)h->emb_rows_loaded, (unsigned long long)h->desc.n_docs);
   if (nq == 0) return OI_OK;
   u64 *local = local_only ? local_only : (h->world > 1 ? h->d_keys_local : h->d_keys_cos);
-  if (h->gemm_min_batch > 0 && nq >= (uint32_t)h->gemm_min_batch && oi_gemm_eligible(h, nq, k)) {
+  if (use_gemm(h, nq, k)) {
     // batched bf16 queries: one pass of the matrix through the tensor cores serves the whole batch
-    oi_status s = oi_gemm_local_keys(h, d_queries, nq, k, local, nullptr, st);
+    oi_status s = oi_gemm_local_keys(h, d_queries, nq, k, local, nullptr, st, gemm_lite || h->gemm_force_lite, gemm_ctas);
     if (s) return s;
   } else {
     OI_CK(oi_launch_cosine_scan(h->d_emb, h->desc.dtype, h->desc.n_docs, h->desc.dim, (uint32_t)h->desc.doc_base, d_queries, nq, k,
@@ -294,10 +370,13 @@ extern "C" oi_status oi_search_cosine_dev(oi_index *h, const float *d_queries, u
   oi_status s = check_search_args(h, nq, k);
   if (s) return s;
   OI_REQUIRE(nq == 0 || (d_queries && d_out_ids && d_out_scores), "NULL device pointer");
+  if (nq == 0) return OI_OK;
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  OI_CK(call_begin(h, st));
   if ((s = cosine_keys(h, d_queries, nq, k, st))) return s;
   OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, d_out_ids, d_out_scores, st, &h->launches));
+  OI_CK(call_end(h, st));
   return OI_OK;
 }
 
@@ -311,6 +390,7 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
   if (nq == 0) return OI_OK;
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = h->stream;
+  OI_CK(call_begin(h, st));
   const size_t qbytes = (size_t)nq * h->desc.dim * sizeof(float), n = (size_t)nq * k;
   if (!h->no_pinned_staging && qbytes <= OI_PIN_BYTES && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
     memcpy(h->h_pin_in, queries, qbytes);
@@ -320,6 +400,7 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
     float *d_sc = reinterpret_cast<float *>(h->d_pin_out + n * 4);
     OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, d_ids, d_sc, st, &h->launches));
     OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 8, cudaMemcpyDeviceToHost, st));
+    OI_CK(call_end(h, st));
     OI_CK(cudaStreamSynchronize(st));
     memcpy(out_ids, h->h_pin_out, n * 4);
     memcpy(out_scores, h->h_pin_out + n * 4, n * 4);
@@ -330,6 +411,7 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
   OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, h->d_out_u32, h->d_out_f32, st, &h->launches));
   OI_CK(cudaMemcpyAsync(out_ids, h->d_out_u32, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaMemcpyAsync(out_scores, h->d_out_f32, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OI_CK(call_end(h, st));
   OI_CK(cudaStreamSynchronize(st));
   return OI_OK;
 }
@@ -342,6 +424,7 @@ extern "C" oi_status oi_debug_cosine_gemm_scores(oi_index *h, const float *queri
   if (h->emb_rows_loaded < h->desc.n_docs) return h->fail(OI_ERR_STATE, "embeddings not loaded");
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = h->stream;
+  OI_CK(call_begin(h, st));
   float *d_dump = nullptr;
   const size_t n = (size_t)nq * h->desc.n_docs;
   OI_CK(cudaMalloc(&d_dump, n * sizeof(float)));
@@ -358,32 +441,32 @@ extern "C" oi_status oi_debug_cosine_gemm_scores(oi_index *h, const float *queri
 
 // local BM25 lists -> (multi-GPU: all-gather + merge) -> global BM25 key lists in d_keys_bm25
 static oi_status bm25_keys(oi_index *h, const uint32_t *d_terms, const uint32_t *d_offs, uint32_t nq, uint32_t k, cudaStream_t st,
-                           u64 *local_only = nullptr) {
+                           u64 *local_only = nullptr, int overlap = 0) {
   if (nq == 0) return OI_OK;
   u64 *local = local_only ? local_only : (h->world > 1 ? h->d_keys_local : h->d_keys_bm25);
-  oi_status s = oi_bm25_local_keys(h, d_terms, d_offs, nq, k, local, st);
+  oi_status s = oi_bm25_local_keys(h, d_terms, d_offs, nq, k, local, st, overlap);
   if (s) return s;
   if (h->world > 1 && !local_only) return oi_comm_gather_merge(h, local, nq, k, h->d_keys_bm25, st);
   return OI_OK;
 }
 
-// validates the host-side query term arrays
+// validates the host-side query term arrays.  A query may carry any number of raw term ids: the device de-duplicates
+// them in first-seen order and scores at most the first 64 distinct known terms (SPEC §3) -- the same rule the `_dev`
+// entry points apply, so both paths return the same lists for the same arrays.  Only the size of the whole call is
+// bounded (by the staging array).
 static oi_status check_terms(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq) {
   if (!oi_bm25_stage_terms(h)) return h->fail(OI_ERR_STATE, "no BM25 index loaded");
   OI_REQUIRE(q_offsets != nullptr, "q_offsets is NULL");
   OI_REQUIRE(q_offsets[0] == 0, "q_offsets[0] must be 0");
-  for (uint32_t j = 0; j < nq; ++j) {
-    OI_REQUIRE(q_offsets[j + 1] >= q_offsets[j], "q_offsets not monotone at query %u", j);
-    OI_REQUIRE(q_offsets[j + 1] - q_offsets[j] <= 64, "query %u has %u terms (max 64)", j, q_offsets[j + 1] - q_offsets[j]);
-  }
+  for (uint32_t j = 0; j < nq; ++j) OI_REQUIRE(q_offsets[j + 1] >= q_offsets[j], "q_offsets not monotone at query %u", j);
   OI_REQUIRE(q_offsets[nq] == 0 || q_terms != nullptr, "q_terms is NULL");
+  OI_REQUIRE(q_offsets[nq] <= oi_bm25_stage_capacity(h), "the call carries %u term ids; at most %llu fit (64 x max_batch)", q_offsets[nq],
+             (unsigned long long)oi_bm25_stage_capacity(h));
   return OI_OK;
 }
 
 // ... and stages them on the device (the large-call path; small calls pack them into the pinned block)
 static oi_status stage_terms(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq, cudaStream_t st) {
-  oi_status s = check_terms(h, q_terms, q_offsets, nq);
-  if (s) return s;
   const uint32_t total = q_offsets[nq];
   if (total) OI_CK(cudaMemcpyAsync(oi_bm25_stage_terms(h), q_terms, (size_t)total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   OI_CK(cudaMemcpyAsync(oi_bm25_stage_offs(h), q_offsets, ((size_t)nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -408,10 +491,13 @@ extern "C" oi_status oi_search_bm25_dev(oi_index *h, const uint32_t *d_q_terms, 
   oi_status s = check_search_args(h, nq, k);
   if (s) return s;
   OI_REQUIRE(nq == 0 || (d_q_terms && d_q_offsets && d_out_ids && d_out_scores), "NULL device pointer");
+  if (nq == 0) return OI_OK;
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  OI_CK(call_begin(h, st));
   if ((s = bm25_keys(h, d_q_terms, d_q_offsets, nq, k, st))) return s;
   OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, d_out_ids, d_out_scores, st, &h->launches));
+  OI_CK(call_end(h, st));
   return OI_OK;
 }
 
@@ -426,6 +512,7 @@ extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const 
   OI_CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = h->stream;
   if ((s = check_terms(h, q_terms, q_offsets, nq))) return s;
+  OI_CK(call_begin(h, st));
   const size_t n = (size_t)nq * k;
   size_t o_offs, o_terms;
   const size_t in_bytes = pin_in_layout(0, nq, q_offsets[nq], &o_offs, &o_terms);
@@ -436,6 +523,7 @@ extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const 
     if ((s = bm25_keys(h, reinterpret_cast<const uint32_t *>(h->d_pin_in + o_terms), reinterpret_cast<const uint32_t *>(h->d_pin_in + o_offs), nq, k, st))) return s;
     OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, reinterpret_cast<uint32_t *>(h->d_pin_out), reinterpret_cast<float *>(h->d_pin_out + n * 4), st, &h->launches));
     OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 8, cudaMemcpyDeviceToHost, st));
+    OI_CK(call_end(h, st));
     OI_CK(cudaStreamSynchronize(st));
     memcpy(out_ids, h->h_pin_out, n * 4);
     memcpy(out_scores, h->h_pin_out + n * 4, n * 4);
@@ -446,18 +534,44 @@ extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const 
   OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, h->d_out_u32, h->d_out_f32, st, &h->launches));
   OI_CK(cudaMemcpyAsync(out_ids, h->d_out_u32, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaMemcpyAsync(out_scores, h->d_out_f32, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OI_CK(call_end(h, st));
   OI_CK(cudaStreamSynchronize(st));
   return OI_OK;
 }
 
-// cosine lists + BM25 lists (each global) -> RRF
+// cosine lists + BM25 lists (each global) -> RRF.
+//
+// The two legs are independent until the fusion.  hybrid_overlap = 0 enqueues them back to back on the caller's stream.
+// With the tensor-core cosine path the legs are complementary (GEMM: tensor pipe + HBM, 6 warps; BM25: issue slots +
+// L2, no tensor work), so the other modes fork the BM25 leg onto the handle's second stream and join before the
+// exchange / fusion:
+//   1  co-residency: the GEMM runs its "lite" kernel (96 KB ring, < 128 registers) and the BM25 kernel a CTA of
+//      overlap_bm25_warps warps (128 registers), so that ONE CTA OF EACH fits every SM (shared memory 116 + 106 KB,
+//      registers 24.5 k + 41 k of 64 k).  The GEMM is launched first: its CTAs take their SMs, the BM25 CTAs fill in.
+//   2  SM partition: the stand-alone kernels, the GEMM confined to overlap_gemm_sms SMs, BM25 to the rest.
 static oi_status hybrid_enqueue(oi_index *h, const float *d_queries, const uint32_t *d_terms, const uint32_t *d_offs,
                                 uint32_t nq, uint32_t k, uint32_t rrf_k, uint32_t *d_ids, float *d_rrf, uint32_t *d_rc,
                                 uint32_t *d_rb, cudaStream_t st) {
   oi_status s;
-  if (h->world > 1) {
+  int mode = h->hybrid_overlap;
+  if (mode && (!use_gemm(h, nq, k) || stream_is_capturing(st))) mode = 0;  // the scan path owns every SM: nothing to overlap with
+  if (mode == 1 && !oi_gemm_lite_ok(h)) mode = 0;
+  const bool sharded = h->world > 1;
+  u64 *loc_cos = sharded ? h->d_keys_local : nullptr, *loc_bm = sharded ? h->d_keys_local + (size_t)nq * k : nullptr;
+  if (mode) {
+    cudaStream_t s2 = h->stream2;
+    OI_CK(cudaEventRecord(h->ev_fork, st));
+    OI_CK(cudaStreamWaitEvent(s2, h->ev_fork, 0));
+    const uint32_t gemm_ctas = mode == 2 ? (uint32_t)h->overlap_gemm_sms : 0u;
+    if ((s = cosine_keys(h, d_queries, nq, k, st, loc_cos, mode == 1, gemm_ctas))) return s;
+    if ((s = bm25_keys(h, d_terms, d_offs, nq, k, s2, loc_bm, mode))) return s;
+    OI_CK(cudaEventRecord(h->ev_join, s2));
+    OI_CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    if (sharded) {
+      if ((s = oi_comm_gather_merge2(h, h->d_keys_local, nq, k, h->d_keys_cos, h->d_keys_bm25, st))) return s;
+    }
+  } else if (sharded) {
     // sharded: both local lists first, then ONE exchange for the two modalities (SPEC §5: RRF on the global ranks)
-    u64 *loc_cos = h->d_keys_local, *loc_bm = h->d_keys_local + (size_t)nq * k;
     if ((s = cosine_keys(h, d_queries, nq, k, st, loc_cos))) return s;
     if ((s = bm25_keys(h, d_terms, d_offs, nq, k, st, loc_bm))) return s;
     if ((s = oi_comm_gather_merge2(h, h->d_keys_local, nq, k, h->d_keys_cos, h->d_keys_bm25, st))) return s;
@@ -481,7 +595,11 @@ extern "C" oi_status oi_search_hybrid_dev(oi_index *h, const float *d_queries, c
   OI_REQUIRE(nq == 0 || (d_queries && d_q_terms && d_q_offsets && d_out_ids && d_out_rrf && d_out_rank_cos && d_out_rank_bm25), "NULL device pointer");
   if (nq == 0) return OI_OK;
   OI_CK(cudaSetDevice(h->desc.device));
-  return hybrid_enqueue(h, d_queries, d_q_terms, d_q_offsets, nq, k, rrf_k, d_out_ids, d_out_rrf, d_out_rank_cos, d_out_rank_bm25, (cudaStream_t)cuda_stream);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  OI_CK(call_begin(h, st));
+  if ((s = hybrid_enqueue(h, d_queries, d_q_terms, d_q_offsets, nq, k, rrf_k, d_out_ids, d_out_rrf, d_out_rank_cos, d_out_rank_bm25, st))) return s;
+  OI_CK(call_end(h, st));
+  return OI_OK;
 }
 
 extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const uint32_t *q_terms, const uint32_t *q_offsets,
@@ -499,6 +617,7 @@ extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const u
   const size_t n = (size_t)nq * k, BK = (size_t)h->desc.max_batch * h->desc.max_k;
   const size_t qbytes = (size_t)nq * h->desc.dim * sizeof(float);
   if ((s = check_terms(h, q_terms, q_offsets, nq))) return s;
+  OI_CK(call_begin(h, st));
   size_t o_offs, o_terms;
   const size_t in_bytes = pin_in_layout(qbytes, nq, q_offsets[nq], &o_offs, &o_terms);
   if (!h->no_pinned_staging && in_bytes && n * 16 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
@@ -512,6 +631,7 @@ extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const u
                             reinterpret_cast<const uint32_t *>(h->d_pin_in + o_offs), nq, k, rrf_k, d_ids, d_rrf, d_rc, d_rb, st)))
       return s;
     OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 16, cudaMemcpyDeviceToHost, st));
+    OI_CK(call_end(h, st));
     OI_CK(cudaStreamSynchronize(st));
     memcpy(out_ids, h->h_pin_out, n * 4);
     memcpy(out_rrf, h->h_pin_out + n * 4, n * 4);
@@ -527,6 +647,7 @@ extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const u
   OI_CK(cudaMemcpyAsync(out_rrf, h->d_out_f32, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaMemcpyAsync(out_rank_cos, d_rc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OI_CK(cudaMemcpyAsync(out_rank_bm25, d_rb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  OI_CK(call_end(h, st));
   OI_CK(cudaStreamSynchronize(st));
   return OI_OK;
 }

@@ -550,53 +550,51 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
   }
 }
 
-// sorts each query's terms ascending, drops duplicates, unknown terms and empty lists.  One warp per query: lane l
-// looks at input terms l and 32 + l (all list-length loads in flight at once), then every valid first occurrence
-// ranks itself among the others with shuffles -- a single query used to spend 8 us here on serial dependent loads.
+// Query preparation, one warp per query: de-duplicates the raw term ids in first-seen order, drops unknown terms and
+// empty lists, keeps at most the first 64 distinct known terms (SPEC §3) and writes them in ascending term id.  A
+// query may carry any number of raw ids (the host-buffer and the `_dev` entry points behave alike); the usual 8-term
+// query is one 32-id chunk: all list-length loads in flight at once, then ranks by counting.
 __global__ void __launch_bounds__(128) bm25_prep_queries_kernel(const uint32_t *q_terms, const uint32_t *q_offs, uint32_t nq,
                                                                const u64 *term_off, uint32_t n_terms, uint32_t *out_terms,
                                                                uint32_t *out_nt, u64 *gthr, uint32_t *counter) {
+  __shared__ uint32_t s_kept[4][OI_BM25_MAX_QTERMS];
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t *kept = s_kept[threadIdx.x >> 5];
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
   if (q >= nq) return;  // warp-uniform
   if (lane == 0) gthr[q] = 0ull;
   const uint32_t lo = q_offs[q];
-  uint32_t n_in = q_offs[q + 1] - lo;
-  if (n_in > OI_BM25_MAX_QTERMS) n_in = OI_BM25_MAX_QTERMS;
-  uint32_t t[2];
-  bool ok[2];
+  const uint32_t n_in = q_offs[q + 1] - lo;
+  uint32_t n_kept = 0;
+  for (uint32_t c0 = 0; c0 < n_in && n_kept < OI_BM25_MAX_QTERMS; c0 += 32) {
+    const uint32_t i = c0 + (uint32_t)lane;
+    const uint32_t t = i < n_in ? q_terms[lo + i] : 0xFFFFFFFFu;
+    bool ok = i < n_in && t < n_terms;
+    if (ok) ok = term_off[t + 1] != term_off[t];
+    for (uint32_t j = 0; j < n_kept; ++j)  // already kept by an earlier chunk
+      if (kept[j] == t) ok = false;
+    const uint32_t same = __match_any_sync(0xFFFFFFFFu, t);
+    const bool first = ok && (same & ((1u << lane) - 1u)) == 0u;  // first occurrence inside the chunk
+    const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
+    const uint32_t pos = n_kept + (uint32_t)__popc(fm & ((1u << lane) - 1u));
+    if (first && pos < OI_BM25_MAX_QTERMS) kept[pos] = t;
+    n_kept = min((uint32_t)OI_BM25_MAX_QTERMS, n_kept + (uint32_t)__popc(fm));
+    __syncwarp();
+  }
+  // rank = number of kept terms below mine
+  uint32_t *o = out_terms + (size_t)q * OI_BM25_MAX_QTERMS;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const uint32_t i = (uint32_t)lane + 32u * hh;
-    t[hh] = i < n_in ? q_terms[lo + i] : 0xFFFFFFFFu;
-    ok[hh] = i < n_in && t[hh] < n_terms;
-    if (ok[hh]) ok[hh] = term_off[t[hh] + 1] != term_off[t[hh]];
+    if (i < n_kept) {
+      const uint32_t t = kept[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < n_kept; ++j) rank += kept[j] < t;
+      o[rank] = t;
+    }
   }
-  // first occurrence of its value among the valid inputs (input order)
-  bool first[2] = {ok[0], ok[1]};
-  for (uint32_t j = 0; j < n_in; ++j) {
-    const uint32_t tj = __shfl_sync(0xFFFFFFFFu, j < 32 ? t[0] : t[1], (int)(j & 31));
-    const bool okj = __shfl_sync(0xFFFFFFFFu, (int)(j < 32 ? ok[0] : ok[1]), (int)(j & 31)) != 0;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh)
-      if (okj && tj == t[hh] && j < (uint32_t)lane + 32u * hh) first[hh] = false;
-  }
-  // rank = number of kept terms below mine
-  uint32_t rank[2] = {0, 0};
-  for (uint32_t j = 0; j < n_in; ++j) {
-    const uint32_t tj = __shfl_sync(0xFFFFFFFFu, j < 32 ? t[0] : t[1], (int)(j & 31));
-    const bool kj = __shfl_sync(0xFFFFFFFFu, (int)(j < 32 ? first[0] : first[1]), (int)(j & 31)) != 0;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh)
-      if (kj && tj < t[hh]) ++rank[hh];
-  }
-  uint32_t *o = out_terms + (size_t)q * OI_BM25_MAX_QTERMS;
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh)
-    if (first[hh]) o[rank[hh]] = t[hh];
-  const uint32_t n = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, first[0])) + (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, first[1]));
-  if (lane == 0) out_nt[q] = n;
+  if (lane == 0) out_nt[q] = n_kept;
 }
 
 // per-posting folded weight, SPEC §3 association, one IEEE op per line (file built with -fmad=false)
@@ -1029,11 +1027,12 @@ extern "C" oi_status oi_index_read_bm25(oi_index *h, uint64_t *term_offsets, uin
 uint32_t oi_bm25_n_terms(const oi_index *h) { return h->bm25 ? h->bm25->n_terms : 0; }
 uint32_t *oi_bm25_stage_terms(oi_index *h) { return h->bm25 ? h->bm25->d_in_terms : nullptr; }
 uint32_t *oi_bm25_stage_offs(oi_index *h) { return h->bm25 ? h->bm25->d_in_offs : nullptr; }
+size_t oi_bm25_stage_capacity(const oi_index *h) { return (size_t)h->desc.max_batch * OI_BM25_MAX_QTERMS; }
 
 // Enqueues: prep -> blocked scoring -> per-query merge of the S lists into d_out_keys [nq][k]
 // (shard-local result, keys carry global doc ids).
 oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint32_t *d_q_offs, uint32_t nq,
-                             uint32_t k, u64 *d_out_keys, cudaStream_t st) {
+                             uint32_t k, u64 *d_out_keys, cudaStream_t st, int overlap) {
   OiBm25 *b = h->bm25;
   if (!b || !b->finalized) return h->fail(OI_ERR_STATE, "BM25 index not loaded / not finalized");
   if (nq == 0) return OI_OK;
@@ -1071,9 +1070,13 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   }
   if (h->bm25_warps > 0) ng = (uint32_t)h->bm25_warps;
   if (h->bm25_block_docs > 0) p.R = (uint32_t)h->bm25_block_docs;
+  // hybrid overlap mode 1: a CTA small enough (warps x 128 registers, ~106 KB) to share its SM with a GEMM CTA
+  const bool lite = overlap == 1 && cap <= 256;
+  if (lite) { ng = (uint32_t)h->overlap_bm25_warps; p.R = 2048; }
   if (ng > 24 || p.R < 1024 || (p.R & (p.R - 1)) || smem_for(ng, p.R, 0) > smem_max)
     return h->fail(OI_ERR_INVALID_ARG, "BM25 tuning: %u warps x %u-document blocks (k = %u) do not fit one SM", ng, p.R, k);
   uint32_t nslot = h->bm25_stage_slots >= 0 ? (uint32_t)h->bm25_stage_slots : 8;
+  if (lite) nslot = (uint32_t)h->overlap_bm25_slots;
   while (nslot > 0 && smem_for(ng, p.R, nslot) > smem_max) --nslot;
   p.nslot = nslot;
   p.cold_bound = (k <= 256 && nslot >= 2 && !h->bm25_no_cold_bound) ? 1u : 0u;
@@ -1082,7 +1085,10 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   while ((1u << p.r_shift) < p.R) ++p.r_shift;
   p.n_blocks = (p.n_docs + p.R - 1) / p.R;
   if (p.n_blocks == 0) p.n_blocks = 1;
-  const uint32_t groups = (uint32_t)h->num_sms * ng;
+  // one CTA per SM (overlap mode 2: only on the SMs the GEMM leaves free)
+  uint32_t grid = (uint32_t)h->num_sms;
+  if (overlap == 2) grid = (uint32_t)std::max(1, h->num_sms - h->overlap_gemm_sms);
+  const uint32_t groups = grid * ng;
   // super-ranges per query: enough work items (S x nq) for every warp to take ~16, so that the last items to finish
   // (queries differ a lot in cost: zero to several dense terms) leave the SMs idle for a small part of the launch
   const uint32_t ipw = h->bm25_items_per_warp > 0 ? (uint32_t)h->bm25_items_per_warp : 16;
@@ -1105,7 +1111,6 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   }
   // one CTA per SM; with fewer items than SMs x warps the items still spread over all SMs (each SM's first warps
   // to reach the counter take them): a single query is latency-bound and every SM brings its own load pipes
-  uint32_t grid = (uint32_t)h->num_sms;
   if (grid > p.S * nq) grid = p.S * nq;
   if (ng > 16 && ng <= 18 && p.R == 2048) bm25_blocked_kernel<576, 2048><<<grid, ng * 32, smem, st>>>(p);
   else if (ng > 18 && ng <= 20 && p.R == 2048) bm25_blocked_kernel<640, 2048><<<grid, ng * 32, smem, st>>>(p);

@@ -21,9 +21,11 @@
 // query's running threshold; only when the maximum passes does it look at individual scores and
 // append (score, doc) keys to the (CTA, query) candidate list in global memory.  A list that
 // could overflow is compacted to its best k by the warp (bitonic sort in shared memory) and the
-// threshold raised.  A first short pass over a sample of the shard gives every query the exact
-// k-th best key of the sample as a starting threshold for the main pass, so in the main pass only
-// a handful of scores per (CTA, query) ever pass the filter.
+// threshold raised.  A first short PROBE pass over a strided sample of the shard's tiles (~1 % of
+// them) only records the maxima of groups of 8 scores; the k-th largest group maximum is a score
+// at least k documents reach, i.e. a valid lower bound of every query's k-th best score, and seeds
+// the one MAIN pass over all tiles, in which only a handful of scores per (CTA, query) pass the
+// filter.  (Round 1 used five passes of growing size, each with its own merge launch.)
 //
 //   algorithmic bytes per batch = n_docs * dim * 2        flops per batch = 2 * n_docs * dim * nq
 #include <cuda.h>
@@ -62,7 +64,9 @@ constexpr uint32_t kMaxDim = 768;     // dim / 2 columns of TMEM hold the query 
 struct GemmParams {
   const __nv_bfloat16 *qb;
   uint32_t n_rows, dim, doc_base, k, nq, n_qt, n_ranges;
-  uint32_t tile_begin, tile_end;  // document tiles [begin, end) covered by this launch
+  uint32_t tile_begin, tile_end;  // logical tiles [begin, end) covered by this launch; physical tile = logical * tile_mul
+  uint32_t tile_mul;              // 1 for the main pass, the sampling stride for the probe pass
+  uint32_t probe;                 // 1: record only the maxima of groups of 8 scores (score-only keys) for the threshold
   const u64 *thr_in;              // [nq] starting threshold keys (0 = none) or nullptr
   u64 *cand;                      // [grid * 128][cap]
   uint32_t *cand_cnt;             // [grid * 128]
@@ -104,16 +108,18 @@ __device__ __forceinline__ u64 warp_compact_list(u64 *list, uint32_t n, uint32_t
 // Ring geometry for a row of NKB k-blocks (dim = 64 * NKB): the 192 KB ring holds 24 slabs of
 // 64 rows x 128 B.  A stage = KBS slabs (one TMA op, one mbarrier); a tile = SPT stages; the ring
 // holds TIF whole tiles, so inside a group of TIF tiles every stage index is a compile-time constant.
-template <int NKB>
+// RING = slabs in the ring: 24 (192 KB, the stand-alone kernel) or 12 (96 KB, the "lite" kernel that shares an SM
+// with a BM25 CTA when the hybrid call overlaps its two legs).
+template <int NKB, int RING>
 struct GemmShape {
-  static_assert(24 % NKB == 0, "dim / 64 must divide 24");
+  static_assert(RING % NKB == 0, "dim / 64 must divide the ring");
   static constexpr int KBS = (NKB % 4 == 0) ? 4 : (NKB % 2 == 0) ? 2 : 1;
   static constexpr int SPT = NKB / KBS;
-  static constexpr int TIF = 24 / NKB;
+  static constexpr int TIF = RING / NKB;
   static constexpr int STAGES = SPT * TIF;
   static constexpr uint32_t STAGE_BYTES = KBS * 8192u;
+  static constexpr uint32_t RING_BYTES = RING * 8192u;
 };
-constexpr uint32_t kRingBytes = 24 * 8192;
 constexpr uint32_t kMaxStages = 24;
 
 __device__ __forceinline__ uint32_t oi_elect_one() {
@@ -128,15 +134,14 @@ __device__ __forceinline__ uint32_t oi_elect_one() {
   return pred;
 }
 
-template <int NKB>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-    cosine_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
-  using Sh = GemmShape<NKB>;
+template <int NKB, int RING>
+__device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const GemmParams &p) {
+  using Sh = GemmShape<NKB, RING>;
   constexpr int KBS = Sh::KBS, SPT = Sh::SPT, TIF = Sh::TIF, STAGES = Sh::STAGES;
   extern __shared__ unsigned char s_raw[];
   unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char *s_stage = sm;                                                   // 24 slabs x 8 KB, 1024 B aligned
-  u64 *s_scratch = reinterpret_cast<u64 *>(sm + kRingBytes);                     // 4 warps x cap keys
+  unsigned char *s_stage = sm;                                                   // RING slabs x 8 KB, 1024 B aligned
+  u64 *s_scratch = reinterpret_cast<u64 *>(sm + Sh::RING_BYTES);                 // 4 warps x cap keys
   u64 *s_full = s_scratch + 4 * kCapMax;
   u64 *s_empty = s_full + kMaxStages;
   u64 *s_tfull = s_empty + kMaxStages;  // [2] accumulator ready
@@ -185,12 +190,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               oi_mbar_expect_tx(&s_full[s], Sh::STAGE_BYTES);
               // rows past the end of the shard are zero-filled by the TMA unit
               if (p.tma3d) {
-                oi_tma_load_3d(s_stage + (size_t)s * Sh::STAGE_BYTES, &tmap, 0, (int32_t)(t * kTileDocs), j * KBS, &s_full[s]);
+                oi_tma_load_3d(s_stage + (size_t)s * Sh::STAGE_BYTES, &tmap, 0, (int32_t)(t * p.tile_mul * kTileDocs), j * KBS, &s_full[s]);
               } else {
 #pragma unroll
                 for (int kk = 0; kk < KBS; ++kk)
                   oi_tma_load_2d(s_stage + (size_t)s * Sh::STAGE_BYTES + kk * 8192, &tmap, (j * KBS + kk) * (int)kKBlock,
-                                 (int32_t)(t * kTileDocs), &s_full[s]);
+                                 (int32_t)(t * p.tile_mul * kTileDocs), &s_full[s]);
               }
             }
           }
@@ -253,16 +258,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // warp is 4 KB contiguous, 128 B per lane
       const uint32_t n_chunks = p.dim / 64;
       const uint4 *qsrc = reinterpret_cast<const uint4 *>(p.qb) + ((size_t)(qt * 4 + quarter) * n_chunks * 32 + lane) * 8;
-      uint4 x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = __ldg(qsrc + j);
-      for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+      for (uint32_t ch = 0; ch < n_chunks; ++ch) {  // once per launch: no prefetch, 32 live registers
         uint32_t r[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { r[4 * j] = x[j].x; r[4 * j + 1] = x[j].y; r[4 * j + 2] = x[j].z; r[4 * j + 3] = x[j].w; }
-        if (ch + 1 < n_chunks) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = __ldg(qsrc + (size_t)(ch + 1) * 256 + j);
+        for (int j = 0; j < 8; ++j) {
+          const uint4 x = __ldg(qsrc + (size_t)ch * 256 + j);
+          r[4 * j] = x.x; r[4 * j + 1] = x.y; r[4 * j + 2] = x.z; r[4 * j + 3] = x.w;
         }
         oi_tmem_st32(lane_taddr + ch * 32, r);
       }
@@ -285,53 +286,65 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const uint32_t b = tl & 1u, bph = (tl >> 1) & 1u;
       oi_mbar_wait(&s_tfull[b], bph);
       oi_tc_fence_after();
-      uint32_t v[64];
-      oi_tmem_ld32(lane_taddr + kDCol0 + b * kTileDocs, v);
-      oi_tmem_ld32(lane_taddr + kDCol0 + b * kTileDocs + 32, v + 32);
-      oi_tmem_wait_ld();
-      oi_tc_fence_before();
-      __syncwarp();
-      if (lane == 0) oi_mbar_arrive(&s_tempty[b]);  // the accumulator may be overwritten: scores are in registers
-
-      const uint32_t doc0 = t * kTileDocs;
+      const uint32_t doc0 = t * p.tile_mul * kTileDocs;
       const uint32_t n_valid = min(kTileDocs, p.n_rows - doc0);
-      if (n_valid < kTileDocs) {  // last tile of the shard: columns past the end never qualify
+      // the 64 scores of the tile are taken in two halves of 32 columns (32 live registers instead of 64: the kernel
+      // stays below 128 registers per thread, so a BM25 CTA fits next to it on the SM)
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if ((uint32_t)i >= n_valid) v[i] = 0x7FC00000u;  // NaN: loses every fmaxf and every >= compare
-      }
-      if (qv && !(p.debug & 4u)) {
-        if (p.dump) {
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        oi_tmem_ld32(lane_taddr + kDCol0 + b * kTileDocs + hf * 32, v);
+        oi_tmem_wait_ld();
+        if (n_valid < kTileDocs) {  // last tile of the shard: columns past the end never qualify
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if ((uint32_t)i < n_valid) p.dump[(size_t)q * p.n_rows + doc0 + i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i)
+            if ((uint32_t)(hf * 32 + i) >= n_valid) v[i] = 0x7FC00000u;  // NaN: loses every fmaxf and every >= compare
         }
-        // two-level filter: maxima of 8 groups of 8 scores, then their maximum.  Most tiles stop at
-        // the single compare; a tile with a survivor only opens the groups that hold one.
-        float gm[8];
+        if (qv && !(p.debug & 4u)) {
+          if (p.dump) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float a = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
-          const float b = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
-          gm[g] = fmaxf(fmaxf(a, b), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-        }
-        const float m = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])), fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
-        if (m >= thr_s) {
+            for (int i = 0; i < 32; ++i)
+              if ((uint32_t)(hf * 32 + i) < n_valid) p.dump[(size_t)q * p.n_rows + doc0 + hf * 32 + i] = __uint_as_float(v[i]);
+          }
+          // two-level filter: maxima of 4 groups of 8 scores, then their maximum.  Most tiles stop at the single
+          // compare; a tile with a survivor only opens the groups that hold one.
+          float gm[4];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (gm[g] >= thr_s) {
+          for (int g = 0; g < 4; ++g) {
+            const float a = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+            const float c = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
+            gm[g] = fmaxf(fmaxf(a, c), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+          }
+          if (p.probe) {
+            // probe pass: a group maximum is the score of one real document and the groups are disjoint, so the k-th
+            // largest of them is a score at least k documents reach.  Score-only keys (doc field 0).
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float s = __uint_as_float(v[8 * g + e]);
-                if (s >= thr_s) {
-                  const u64 key = oi_make_key(s, p.doc_base + doc0 + 8 * g + e);
-                  if (key > thr_key) { buf[cnt] = key; ++cnt; }
+            for (int g = 0; g < 4; ++g)
+              if (gm[g] == gm[g]) { buf[cnt] = (u64)oi_ord(gm[g]) << 32; ++cnt; }  // NaN = a group past the end of the shard
+          } else {
+            const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+            if (m >= thr_s) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (gm[g] >= thr_s) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float sc = __uint_as_float(v[8 * g + e]);
+                    if (sc >= thr_s) {
+                      const u64 key = oi_make_key(sc, p.doc_base + doc0 + hf * 32 + 8 * g + e);
+                      if (key > thr_key) { buf[cnt] = key; ++cnt; }
+                    }
+                  }
                 }
               }
             }
           }
         }
       }
+      oi_tc_fence_before();
+      __syncwarp();
+      if (lane == 0) oi_mbar_arrive(&s_tempty[b]);  // both halves are in registers / consumed: the accumulator may be overwritten
+
       // a list that could overflow during the next tile is reduced to its best k by the whole warp
       uint32_t mask = __ballot_sync(0xFFFFFFFFu, cnt + kTileDocs > cap);
       while (mask) {
@@ -356,6 +369,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     oi_tc_fence_after();
     oi_tmem_dealloc(tmem, kTmemCols);
   }
+}
+
+// Two entry points over the same body.  The stand-alone kernel owns its SM (192 KB ring, any register count).  The
+// "lite" kernel (96 KB ring) is capped at 128 registers per thread so that 192 x 128 = 24.5 k registers and 116 KB of
+// shared memory leave room on the SM for one BM25 CTA (hybrid overlap, api.cu).
+template <int NKB, int RING>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    cosine_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+  cosine_gemm_body<NKB, RING>(tmap, p);
+}
+template <int NKB, int RING>
+__global__ void __maxnreg__(128)
+    cosine_gemm_lite_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+  cosine_gemm_body<NKB, RING>(tmap, p);
 }
 
 // f32 queries -> bf16 pairs (RNE, SPEC §2), zero rows up to a multiple of 128, stored in the order the
@@ -471,8 +498,8 @@ __global__ void __launch_bounds__(256) gemm_merge_kernel(const u64 *cand, const 
   if (thr_out && tid == 0) thr_out[q] = (S.cnt == k) ? S.buf[k - 1] : 0ull;
 }
 
-size_t gemm_smem_bytes() {
-  return 1024 + (size_t)kRingBytes + 4 * kCapMax * sizeof(u64) + (2 * kMaxStages + 5) * sizeof(u64) + 16;
+size_t gemm_smem_bytes(int ring) {
+  return 1024 + (size_t)ring * 8192 + 4 * kCapMax * sizeof(u64) + (2 * kMaxStages + 5) * sizeof(u64) + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -548,41 +575,48 @@ static oi_status gemm_prepare(oi_index *h) {
     if (cr != CUDA_SUCCESS) return h->fail(OI_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
     g->tma3d = false;
   }
-  const int smem = (int)gemm_smem_bytes();
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  GM_CK(cudaFuncSetAttribute(cosine_gemm_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem = (int)gemm_smem_bytes(24), smem_lite = (int)gemm_smem_bytes(12);
+#define OI_GEMM_ATTR(KERNEL, NKB, RING, BYTES) GM_CK(cudaFuncSetAttribute(KERNEL<NKB, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES))
+  OI_GEMM_ATTR(cosine_gemm_kernel, 1, 24, smem); OI_GEMM_ATTR(cosine_gemm_kernel, 2, 24, smem); OI_GEMM_ATTR(cosine_gemm_kernel, 3, 24, smem);
+  OI_GEMM_ATTR(cosine_gemm_kernel, 4, 24, smem); OI_GEMM_ATTR(cosine_gemm_kernel, 6, 24, smem); OI_GEMM_ATTR(cosine_gemm_kernel, 8, 24, smem);
+  OI_GEMM_ATTR(cosine_gemm_kernel, 12, 24, smem);
+  OI_GEMM_ATTR(cosine_gemm_lite_kernel, 1, 12, smem_lite); OI_GEMM_ATTR(cosine_gemm_lite_kernel, 2, 12, smem_lite);
+  OI_GEMM_ATTR(cosine_gemm_lite_kernel, 3, 12, smem_lite); OI_GEMM_ATTR(cosine_gemm_lite_kernel, 4, 12, smem_lite);
+  OI_GEMM_ATTR(cosine_gemm_lite_kernel, 6, 12, smem_lite); OI_GEMM_ATTR(cosine_gemm_lite_kernel, 12, 12, smem_lite);
+#undef OI_GEMM_ATTR
   g->ready = true;
   return OI_OK;
 }
 
+// the "lite" kernel (96 KB ring) exists for the row widths whose tile fits it
+bool oi_gemm_lite_ok(const oi_index *h) { return 12 % (h->desc.dim / kKBlock) == 0; }
+
 static oi_status gemm_launch(oi_index *h, uint32_t nq, uint32_t n_qt, uint32_t n_ranges, uint32_t k, uint32_t cap,
-                             uint32_t tile_begin, uint32_t tile_end, const u64 *thr_in, float *dump, cudaStream_t st) {
+                             uint32_t tile_begin, uint32_t tile_end, uint32_t tile_mul, bool probe, const u64 *thr_in, float *dump,
+                             bool lite, cudaStream_t st) {
   OiGemm *g = h->gemm;
   GemmParams p;
   p.qb = g->d_qb;
   p.n_rows = (uint32_t)h->desc.n_docs; p.dim = h->desc.dim; p.doc_base = (uint32_t)h->desc.doc_base;
   p.k = k; p.nq = nq; p.n_qt = n_qt; p.n_ranges = n_ranges;
-  p.tile_begin = tile_begin; p.tile_end = tile_end;
+  p.tile_begin = tile_begin; p.tile_end = tile_end; p.tile_mul = tile_mul; p.probe = probe ? 1u : 0u;
   p.thr_in = thr_in; p.cand = g->d_cand; p.cand_cnt = g->d_cnt; p.cap = cap; p.dump = dump;
   p.debug = (uint32_t)h->gemm_debug;
   p.tma3d = g->tma3d ? 1u : 0u;
   const uint32_t grid = n_ranges * n_qt;
-  const size_t smem = gemm_smem_bytes();
-  switch (h->desc.dim / kKBlock) {
-    case 1: cosine_gemm_kernel<1><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
-    case 2: cosine_gemm_kernel<2><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
-    case 3: cosine_gemm_kernel<3><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
-    case 4: cosine_gemm_kernel<4><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
-    case 6: cosine_gemm_kernel<6><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
-    case 8: cosine_gemm_kernel<8><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
-    case 12: cosine_gemm_kernel<12><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); break;
+  const uint32_t nkb = h->desc.dim / kKBlock;
+  if (lite && 12 % nkb != 0) lite = false;
+  const size_t smem = gemm_smem_bytes(lite ? 12 : 24);
+#define OI_GEMM_GO(NKB)                                                                       \
+  case NKB:                                                                                   \
+    if (lite) cosine_gemm_lite_kernel<(12 % NKB == 0 ? NKB : 12), 12><<<grid, kGemmThreads, smem, st>>>(g->tmap, p); \
+    else cosine_gemm_kernel<NKB, 24><<<grid, kGemmThreads, smem, st>>>(g->tmap, p);           \
+    break;
+  switch (nkb) {
+    OI_GEMM_GO(1) OI_GEMM_GO(2) OI_GEMM_GO(3) OI_GEMM_GO(4) OI_GEMM_GO(6) OI_GEMM_GO(8) OI_GEMM_GO(12)
     default: return h->fail(OI_ERR_UNSUPPORTED, "internal: dim %u has no tensor-core kernel", h->desc.dim);
   }
+#undef OI_GEMM_GO
   ++h->launches;
   GM_CK(cudaGetLastError());
   return OI_OK;
@@ -590,12 +624,13 @@ static oi_status gemm_launch(oi_index *h, uint32_t nq, uint32_t n_qt, uint32_t n
 
 // Shard-local top-k lists d_out_keys[nq][k] (sorted, global doc ids) of nq f32 queries on the device.
 oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, u64 *d_out_keys, float *d_dump,
-                             cudaStream_t st) {
+                             cudaStream_t st, bool lite, uint32_t max_ctas) {
   oi_status s = gemm_prepare(h);
   if (s) return s;
   OiGemm *g = h->gemm;
   const uint32_t n_qt = (nq + 127) / 128;
-  uint32_t n_ranges = (uint32_t)h->num_sms / n_qt;
+  const uint32_t ctas = max_ctas ? std::min<uint32_t>(max_ctas, (uint32_t)h->num_sms) : (uint32_t)h->num_sms;
+  uint32_t n_ranges = ctas / n_qt;
   if (n_ranges < 1) n_ranges = 1;
   const uint32_t n_tiles = (uint32_t)((h->desc.n_docs + kTileDocs - 1) / kTileDocs);
   if (n_ranges > n_tiles) n_ranges = n_tiles;
@@ -609,27 +644,29 @@ oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, u
     ++h->launches;
     GM_CK(cudaGetLastError());
   }
-  // Passes of geometrically growing size (1, 8, 64, ... tiles per CTA).  The first runs without thresholds
-  // and keeps every score, so it is kept short; each later pass starts from the exact k-th best key of
-  // everything scored so far, so the share of tiles in which any score passes the filter keeps shrinking.
-  uint32_t per_range = h->gemm_sample_tiles > 0 ? std::min<uint32_t>((cap - kTileDocs) / kTileDocs, (uint32_t)h->gemm_sample_tiles) : 1u;
-  uint32_t done = 0;
-  const u64 *prev = nullptr;
-  u64 *bufs[2] = {g->d_keys_a, g->d_keys_b};
-  int flip = 0;
-  while (done < n_tiles) {
-    uint64_t n_pass = (uint64_t)n_ranges * per_range;
-    if (d_dump || done + n_pass + n_pass / 4 >= n_tiles) n_pass = n_tiles - done;
-    const bool last = done + n_pass == n_tiles;
-    if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, done, done + (uint32_t)n_pass, prev ? g->d_thr_a : nullptr, d_dump, st))) return s;
-    u64 *out = last ? d_out_keys : bufs[flip];
-    gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, prev, out, last ? nullptr : g->d_thr_a);
+  // Two passes.  PROBE: every CTA scores `pt` tiles of a strided sample of the shard (about 1/128 of its tiles) and
+  // keeps only the maxima of groups of 8 scores; the merge's k-th best of those is a score at least k documents
+  // reach.  MAIN: all tiles, filtered by that bound (a list that still fills up is cut to its best k in the kernel,
+  // which raises its own bound), then the exact top-k of what passed.  Shards with only a few tiles per CTA skip the
+  // probe: their lists hold everything.
+  const uint32_t tiles_per_cta = (n_tiles + n_ranges - 1) / n_ranges;
+  const uint32_t pt_max = std::max<uint32_t>(1u, (cap - kTileDocs) / 8u);
+  uint32_t pt = h->gemm_sample_tiles > 0 ? (uint32_t)h->gemm_sample_tiles : (tiles_per_cta + 127) / 128;
+  pt = std::min(std::max(pt, 1u), pt_max);
+  const bool do_probe = !d_dump && (h->gemm_sample_tiles > 0 || tiles_per_cta >= 8);
+  const u64 *thr = nullptr;
+  if (do_probe) {
+    const uint32_t n_probe = (uint32_t)std::min<uint64_t>((uint64_t)n_ranges * pt, n_tiles);
+    const uint32_t stride = n_tiles / n_probe;
+    if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_probe, stride, true, nullptr, nullptr, lite, st))) return s;
+    gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, g->d_keys_a, g->d_thr_a);
     ++h->launches;
     GM_CK(cudaGetLastError());
-    prev = out;
-    flip ^= 1;
-    done += (uint32_t)n_pass;
-    per_range *= 8;
+    thr = g->d_thr_a;
   }
+  if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_tiles, 1, false, thr, d_dump, lite, st))) return s;
+  gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, d_out_keys, nullptr);
+  ++h->launches;
+  GM_CK(cudaGetLastError());
   return OI_OK;
 }

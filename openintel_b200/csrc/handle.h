@@ -13,12 +13,26 @@ struct oi_index {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   std::mutex mu;       // calls on one handle are serialised (SURVEY §8b threading)
-  std::string err;     // last error message
+  std::string err;     // last error message (read through oi_last_error, which copies it under the lock)
   uint64_t launches = 0;
+  // Every search call uses the handle's single set of workspaces.  The mutex serialises the ENQUEUE; the work of two
+  // calls enqueued on different streams (`_dev` calls on caller streams, host-buffer calls on `stream`) is ordered on
+  // the device by an event recorded at the end of every call and waited for by the next call's stream.
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  // hybrid call: the BM25 leg can run on a second stream next to the cosine GEMM (see api.cu hybrid_enqueue)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int hybrid_overlap = 0;      // 0 = legs back to back on one stream; 1 = co-resident "lite" kernels (GEMM 96 KB ring + BM25 with
+                               // overlap_bm25_warps warps per CTA on every SM); 2 = SM partition (full kernels, overlap_gemm_sms SMs to the GEMM)
+  int overlap_bm25_warps = 10;
+  int overlap_bm25_slots = 1;
+  int overlap_gemm_sms = 74;
 
   // embeddings
   void *d_emb = nullptr;
-  uint64_t emb_rows_loaded = 0;
+  uint64_t emb_rows_loaded = 0;  // rows [0, emb_rows_loaded) hold data: chunks must arrive in order (or overwrite loaded rows)
   int cosine_variant = 1;  // 0 = direct loads, 1 = bulk-copy pipeline with dynamic tiles
   int cosine_multi_query = 2;  // calls with several queries scan the matrix once per group of 4 (rows <= 1536 B): 2 = on the
                                // bulk-copy pipeline where the group fits the registers (f32), 1 = direct loads, 0 = off
@@ -45,7 +59,8 @@ struct oi_index {
   int gemm_cap = 0;            // tests: candidate-list capacity override (0 = default)
   int gemm_force_2d = 0;       // tests: one 2-D TMA box per slab instead of the 3-D view
   int gemm_debug = 0;          // timing experiments only (see GemmParams::debug)
-  int gemm_sample_tiles = 0;   // tests: sample-pass tiles per CTA override (0 = default)
+  int gemm_sample_tiles = 0;   // probe-pass tiles per CTA override (0 = default: 1/128 of the CTA's tiles); > 0 also forces the probe on small shards
+  bool gemm_force_lite = false;  // experiments: always the 96 KB-ring kernel
 
   // BM25
   OiBm25 *bm25 = nullptr;
@@ -71,15 +86,20 @@ void oi_bm25_free(oi_index *h);
 uint32_t *oi_bm25_stage_terms(oi_index *h);  // device staging for the host call's flat term array
 uint32_t *oi_bm25_stage_offs(oi_index *h);
 // prep -> blocked scoring -> merge: shard-local sorted key lists d_out_keys[nq][k] (global doc ids)
+// overlap: 0 = the stand-alone schedule (one CTA per SM, 20 warps); 1 = the "lite" schedule that shares every SM with a
+// GEMM CTA (h->overlap_bm25_warps warps, 128 registers); 2 = full CTAs on the SMs the GEMM leaves free
 oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint32_t *d_q_offs, uint32_t nq,
-                             uint32_t k, u64 *d_out_keys, cudaStream_t st);
+                             uint32_t k, u64 *d_out_keys, cudaStream_t st, int overlap = 0);
+size_t oi_bm25_stage_capacity(const oi_index *h);  // u32 slots of the flat term staging array
 // cosine_gemm.cu
 void oi_gemm_free(oi_index *h);
 bool oi_gemm_eligible(const oi_index *h, uint32_t nq, uint32_t k);
 // shard-local sorted key lists d_out_keys[nq][k] of nq f32 device queries; d_dump (tests) receives the
 // raw nq x n_docs score matrix when not NULL
+// lite: the 96 KB-ring kernel (co-resident with a BM25 CTA); max_ctas: 0 = every SM, else an upper bound of the grid
+bool oi_gemm_lite_ok(const oi_index *h);
 oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, uint32_t k, u64 *d_out_keys, float *d_dump,
-                             cudaStream_t st);
+                             cudaStream_t st, bool lite = false, uint32_t max_ctas = 0);
 // comm.cu
 void oi_comm_destroy(oi_index *h);
 // all-gathers each rank's [nq][k] local lists and merges them into d_out [nq][k] on every rank

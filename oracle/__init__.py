@@ -19,9 +19,12 @@ SEED = 20261018
 
 
 def build(force=False):
-    """Compile oracle/*.c with gcc (oracle/Makefile)."""
-    if force or not os.path.exists(_SO):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    """Compile oracle/*.c with gcc (oracle/Makefile; make rebuilds what is older than its sources)."""
+    if force or not os.path.exists(_SO) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
+            for f in os.listdir(_HERE) if f.endswith((".c", ".h"))):
+        if os.path.exists("/usr/bin/gcc"):
+            subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
 
@@ -227,6 +230,96 @@ def cosine_topk_f32_fast(rows, q, k, n_threads=None):
 
 def max_threads():
     return int(lib().oio_max_threads())
+
+
+def host_threads():
+    """Threads the timed / full-size legs use: every core this process may run on.  NOT omp_get_max_threads():
+    torch.distributed.run exports OMP_NUM_THREADS=1, which made the round-1 CPU arm a 1-thread run at N >= 2."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
+# ---- full-size drivers (oracle_scale.c): oracle.c's own functions, chunked and spread over the host threads ----
+def scale_synth_rows(n, dim, bf16=False, seed=SEED, stream=0, first=0, n_threads=None):
+    out = np.empty((n, dim), dtype=np.uint16 if bf16 else np.float32)
+    lib().oio_scale_synth_rows(u64(seed), u64(stream), u64(first), u64(n), u32(dim), i32(int(bf16)),
+                               i32(n_threads or host_threads()), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def scale_cosine_topk(n_rows, dim, q, k, bf16=False, seed=SEED, first=0, n_threads=None):
+    """exact top-k (double accumulation) of each query over synthetic rows [first, first + n_rows), regenerated in
+    chunks -> (ids [nq][k] global row numbers, scores f64 [nq][k])"""
+    q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, dim)
+    nq = q.shape[0]
+    ids = np.empty((nq, k), dtype=np.uint32)
+    sc = np.empty((nq, k), dtype=np.float64)
+    lib().oio_scale_cosine_topk(u64(seed), u64(first), u64(n_rows), u32(dim), i32(int(bf16)), _p(q, C.c_float), u32(nq), u32(k),
+                                i32(n_threads or host_threads()), _p(ids, C.c_uint32), _p(sc, C.c_double))
+    return ids, sc
+
+
+def scale_bm25_mini_index(n_docs, vocab, terms, cdf=None, seed=SEED, first=0, n_threads=None):
+    """The CSR restricted to `terms` (any iterable of term ids) of synthetic documents [first, first + n_docs), built
+    by regenerating every document's tokens (oio_synth_tokens) -- the oracle's own index of the touched terms, at
+    sizes where the whole CSR would take minutes.  -> dict(terms (ascending), term_offsets, doc_ids, tfs, doc_len,
+    sum_doc_len); mini term id i stands for terms[i], so ascending order is preserved (SPEC §3 summation order)."""
+    L = lib()
+    L.oio_scale_mini_csr_build.restype = C.c_void_p
+    L.oio_scale_mini_csr_size.restype = C.c_uint64
+    L.oio_scale_mini_csr_size.argtypes = [C.c_void_p]
+    if cdf is None:
+        cdf = zipf_cdf(vocab)
+    terms = np.unique(np.asarray(list(terms), dtype=np.uint32))
+    assert len(terms) <= 64
+    obj = L.oio_scale_mini_csr_build(u64(seed), u64(first), u64(n_docs), _p(cdf, C.c_double), u32(vocab), _p(terms, C.c_uint32),
+                                     u32(len(terms)), i32(n_threads or host_threads()))
+    assert obj, "oio_scale_mini_csr_build failed"
+    n = int(L.oio_scale_mini_csr_size(C.c_void_p(obj)))
+    term_off = np.empty(len(terms) + 1, dtype=np.uint64)
+    d = np.empty(max(n, 1), dtype=np.uint32)
+    tf = np.empty(max(n, 1), dtype=np.uint32)
+    sdl = C.c_uint64()
+    L.oio_scale_mini_csr_take(C.c_void_p(obj), _p(term_off, C.c_uint64), _p(d, C.c_uint32), _p(tf, C.c_uint32), C.byref(sdl))
+    return dict(terms=terms, term_offsets=term_off, doc_ids=d[:n], tfs=tf[:n],
+                doc_len=synth_doc_lens(n_docs, seed, first), sum_doc_len=int(sdl.value), cdf=cdf)
+
+
+def scale_bm25_topk(mini, q_terms, k, n_docs_global=None, avgdl=None, df_global=None, doc_base=0):
+    """BM25 top-k of ONE query from a mini index (scale_bm25_mini_index): oracle.c's idf / weights / dense scoring /
+    top-k on the touched terms only.  df_global: df of mini['terms'] over the whole corpus (default: this index)."""
+    terms = mini["terms"]
+    n_docs = len(mini["doc_len"])
+    df = np.diff(mini["term_offsets"]).astype(np.uint32) if df_global is None else np.asarray(df_global, dtype=np.uint32)
+    idf = bm25_idf(n_docs_global or n_docs, df)
+    if avgdl is None:
+        avgdl = float(np.float32(np.float64(mini["sum_doc_len"]) / np.float64(n_docs)))
+    w = bm25_weights(mini["term_offsets"], mini["doc_ids"], mini["tfs"], mini["doc_len"], idf, avgdl=avgdl)
+    pos = np.searchsorted(terms, np.asarray(q_terms, dtype=np.uint32))
+    known = [int(p) for p, t in zip(pos, q_terms) if p < len(terms) and terms[p] == t]
+    s = bm25_score_dense(mini["term_offsets"], mini["doc_ids"], w, np.asarray(known, dtype=np.uint32), n_docs)
+    return topk_f32(s, k, only_positive=True, doc_base=doc_base)
+
+
+def hybrid_batch_fast(rows_bf16, q, term_off, doc_ids, w, q_terms, k, rrf_k=60, n_threads=None):
+    """The timed CPU baseline of one hybrid batch (oracle_fast.c) over a corpus slice."""
+    rows = np.ascontiguousarray(rows_bf16, dtype=np.uint16)
+    q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, rows.shape[1])
+    qt = np.ascontiguousarray(q_terms, dtype=np.uint32)
+    nq = q.shape[0]
+    assert qt.shape[0] == nq
+    ids = np.empty((nq, k), dtype=np.uint32)
+    rrf_ = np.empty((nq, k), dtype=np.float32)
+    rc = np.empty((nq, k), dtype=np.uint32)
+    rb = np.empty((nq, k), dtype=np.uint32)
+    r = lib().oio_hybrid_batch_fast(_p(rows, C.c_uint16), u64(rows.shape[0]), u32(rows.shape[1]), _p(q, C.c_float), u32(nq),
+                                    _p(term_off, C.c_uint64), _p(doc_ids, C.c_uint32), _p(w, C.c_float), u32(len(term_off) - 1),
+                                    _p(qt, C.c_uint32), u32(qt.shape[1]), u32(k), u32(rrf_k), i32(n_threads or host_threads()),
+                                    _p(ids, C.c_uint32), _p(rrf_, C.c_float), _p(rc, C.c_uint32), _p(rb, C.c_uint32))
+    assert r == 0
+    return ids, rrf_, rc, rb
 
 
 def rrf(ids_cos, ids_bm25, k, rrf_k=60):

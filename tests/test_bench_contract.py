@@ -15,7 +15,8 @@ def _run(args, env=None):
 
 
 def test_reference_arm_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    # a small corpus / slice keeps the CPU suite short; the driver runs the defaults (50M docs, 1M-document slice)
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--docs", "400000", "--cpu-slice", "20000"])
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -23,10 +24,21 @@ def test_reference_arm_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
     assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
-    assert "configs[1]" in d["config"]["workload"] and "model" not in d["config"]
+    assert "hybrid" in d["metric"] and "hybrid BM25+cosine+RRF" in d["config"]["workload"] and "model" not in d["config"]
+    assert d["dtype"] == "bf16" and d["config"]["n_docs"] == 400000
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["sample"]
+    # every host core, also under torch.distributed.run (which exports OMP_NUM_THREADS=1: VERDICT r1)
+    assert cb["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_ignores_omp_num_threads():
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--docs", "400000", "--cpu-slice", "20000"], env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["n_gpus"] == 2
 
 
 def test_reference_arm_other_ranks_exit_quietly():

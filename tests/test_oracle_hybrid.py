@@ -4,6 +4,7 @@ of the same SPEC paragraph on small seeded inputs."""
 import math
 
 import numpy as np
+import pytest
 
 import oracle as O
 
@@ -182,3 +183,56 @@ def test_rrf_against_python_model():
             assert (ids[i], rc[i], rb[i]) == (d, x, y)
             assert val[i].view(np.uint32) == s.view(np.uint32)
         assert all(ids[m:] == O.NO_DOC)
+
+
+# ---- full-size drivers (oracle/oracle_scale.c) and the timed CPU arm (oracle/oracle_fast.c) ----------------------
+def test_scale_rows_and_cosine_topk_equal_the_direct_oracle():
+    """the chunked, multi-threaded drivers return exactly what oracle.c returns in one piece"""
+    assert np.array_equal(O.scale_synth_rows(5000, 128, bf16=True, first=7), O.synth_rows_bf16(5000, 128, first=7))
+    assert np.array_equal(O.scale_synth_rows(3000, 64, first=3, n_threads=3), O.synth_rows_f32(3000, 64, first=3))
+    q = O.synth_rows_f32(3, 128, stream=1)
+    for bf16 in (True, False):
+        rows = O.synth_rows_bf16(30000, 128, first=11) if bf16 else O.synth_rows_f32(30000, 128, first=11)
+        ids, sc = O.scale_cosine_topk(30000, 128, q, 10, bf16=bf16, first=11)
+        for j in range(3):
+            all_sc = O.cosine_scores_bf16(rows, q[j]) if bf16 else O.cosine_scores_f32(rows, q[j])
+            wi, ws, _ = O.topk_f64(all_sc, 10, doc_base=11)
+            assert np.array_equal(wi, ids[j]) and np.array_equal(ws, sc[j])
+
+
+@pytest.mark.parametrize("n_threads", [1, 3, 8])
+def test_mini_index_scores_like_the_whole_csr(n_threads):
+    """the CSR restricted to the touched terms (what the full-size GPU tests check BM25 against) holds exactly the
+    whole CSR's lists of those terms, and scores / ranks bit for bit like the whole index"""
+    n, vocab = 30000, 5000
+    corp = O.synth_bm25_corpus(n, vocab)
+    qt = np.concatenate([O.synth_query_terms(3, 8, corp["cdf"]), O.synth_query_terms(1, 8, corp["cdf"], uniform=True)])
+    mini = O.scale_bm25_mini_index(n, vocab, qt.reshape(-1), cdf=corp["cdf"], n_threads=n_threads)
+    assert mini["sum_doc_len"] == int(corp["doc_len"].sum()) and np.array_equal(mini["doc_len"], corp["doc_len"])
+    for i, t in enumerate(mini["terms"]):
+        a, b = int(corp["term_offsets"][t]), int(corp["term_offsets"][t + 1])
+        c, d = int(mini["term_offsets"][i]), int(mini["term_offsets"][i + 1])
+        assert np.array_equal(corp["doc_ids"][a:b], mini["doc_ids"][c:d]) and np.array_equal(corp["tfs"][a:b], mini["tfs"][c:d])
+    w = O.bm25_weights(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"], O.bm25_idf(n, np.diff(corp["term_offsets"])))
+    for j in range(4):
+        s = O.bm25_score_dense(corp["term_offsets"], corp["doc_ids"], w, qt[j], n)
+        wi, ws, _ = O.topk_f32(s, 20, only_positive=True)
+        gi, gs, _ = O.scale_bm25_topk(mini, qt[j], 20)
+        assert np.array_equal(wi, gi) and np.array_equal(ws.view(np.uint32), gs.view(np.uint32))
+
+
+def test_cpu_arm_hybrid_batch_ranks_like_the_oracle():
+    """the timed CPU baseline (f32 accumulation, blocked, OpenMP) returns the oracle's fused lists on a corpus where
+    no two cosine scores are closer than the f32 / f64 accumulation difference"""
+    n, vocab, dim, k = 20000, 3000, 128, 10
+    corp = O.synth_bm25_corpus(n, vocab)
+    w = O.bm25_weights(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"], O.bm25_idf(n, np.diff(corp["term_offsets"])))
+    rows = O.synth_rows_bf16(n, dim)
+    q = O.synth_rows_f32(4, dim, stream=1)
+    qt = O.synth_query_terms(4, 8, corp["cdf"])
+    ids, rrf, rc, rb = O.hybrid_batch_fast(rows, q, corp["term_offsets"], corp["doc_ids"], w, qt, k, n_threads=3)
+    for j in range(4):
+        ci, _, _ = O.topk_f64(O.cosine_scores_bf16(rows, q[j]), k)
+        bi, _, _ = O.topk_f32(O.bm25_score_dense(corp["term_offsets"], corp["doc_ids"], w, qt[j], n), k, only_positive=True)
+        e = O.rrf(ci, bi, k)
+        assert np.array_equal(e[0], ids[j]) and np.array_equal(e[2], rc[j]) and np.array_equal(e[3], rb[j])
