@@ -24,8 +24,13 @@
 // threshold raised.  A first short PROBE pass over a strided sample of the shard's tiles (~1 % of
 // them) only records the maxima of groups of 8 scores; the k-th largest group maximum is a score
 // at least k documents reach, i.e. a valid lower bound of every query's k-th best score, and seeds
-// the one MAIN pass over all tiles, in which only a handful of scores per (CTA, query) pass the
-// filter.  (Round 1 used five passes of growing size, each with its own merge launch.)
+// the one MAIN pass over all tiles.  The probe's merge also hands out a LADDER of tighter candidate
+// bounds per query (its k/2-th, k/4-th, ... best group maximum).  During the main pass every score
+// that passes the filter is counted, grid-wide, against the rungs above the current one
+// (atomicAdd on 8 counters per query); as soon as k documents have reached a rung it is a valid
+// bound too, and every CTA that polls the counter moves its filter up.  The filter so tightens
+// geometrically while the pass runs -- about k survivors per rung, ~1000 keys per query in total --
+// without any further launch.  (Round 1 used five passes of growing size, each with its own merge.)
 //
 //   algorithmic bytes per batch = n_docs * dim * 2        flops per batch = 2 * n_docs * dim * nq
 #include <cuda.h>
@@ -43,7 +48,8 @@ struct OiGemm {
   uint32_t *d_cnt = nullptr;      // [max_lists]
   u64 *d_keys_a = nullptr;        // [max_batch][max_k] running result after a pass (ping)
   u64 *d_keys_b = nullptr;        // (pong)
-  u64 *d_thr_a = nullptr;         // [max_batch]
+  float *d_lvl_thr = nullptr;     // [max_batch][8] threshold ladder (ascending scores; -inf / +inf = no rung)
+  uint32_t *d_lvl_cnt = nullptr;  // [max_batch][8] documents that reached a rung (main pass, grid-wide)
   uint32_t cap = 0;
   size_t max_lists = 0;
   CUtensorMap tmap;
@@ -60,6 +66,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kDCol0 = 384;      // two 64-column accumulators at 384 and 448
 constexpr uint32_t kCapMax = 512;     // keys per (CTA, query) candidate list
 constexpr uint32_t kMaxDim = 768;     // dim / 2 columns of TMEM hold the query tile
+constexpr uint32_t kLevels = 8;       // rungs of the threshold ladder
 
 struct GemmParams {
   const __nv_bfloat16 *qb;
@@ -67,7 +74,8 @@ struct GemmParams {
   uint32_t tile_begin, tile_end;  // logical tiles [begin, end) covered by this launch; physical tile = logical * tile_mul
   uint32_t tile_mul;              // 1 for the main pass, the sampling stride for the probe pass
   uint32_t probe;                 // 1: record only the maxima of groups of 8 scores (score-only keys) for the threshold
-  const u64 *thr_in;              // [nq] starting threshold keys (0 = none) or nullptr
+  const float *lvl_thr;           // [nq][8] threshold ladder of the main pass (rung 0 = the probe's bound) or nullptr
+  uint32_t *lvl_cnt;              // [nq][8] grid-wide counters of the documents that reached rungs 1..7
   u64 *cand;                      // [grid * 128][cap]
   uint32_t *cand_cnt;             // [grid * 128]
   uint32_t cap;
@@ -278,12 +286,22 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
     u64 *buf = p.cand + list * cap;
     u64 *scratch = s_scratch + (size_t)(warp - 2) * kCapMax;
     uint32_t cnt = 0;
-    u64 thr_key = (qv && p.thr_in) ? p.thr_in[q] : 0ull;
-    float thr_s = thr_key ? oi_key_score(thr_key) : -INFINITY;
+    // threshold ladder: rung 0 is valid from the start, rung lv + 1 once its grid-wide counter reaches k
+    const bool ladder = qv && p.lvl_thr != nullptr && !p.probe;
+    const float *my_lvl = p.lvl_thr + (size_t)(qv ? q : 0) * kLevels;
+    uint32_t *my_cnt = p.lvl_cnt + (size_t)(qv ? q : 0) * kLevels;
+    uint32_t lv = 0;
+    float thr_s = ladder ? __ldg(my_lvl) : -INFINITY;
+    float nxt_s = ladder ? __ldg(my_lvl + 1) : INFINITY;  // the rung being counted
+    u64 thr_key = (ladder && thr_s > -INFINITY) ? ((u64)oi_ord(thr_s) << 32) : 0ull;
 
     uint32_t tl = 0;
     for (uint32_t t = t0; t < p.tile_end; t += p.n_ranges, ++tl) {
       const uint32_t b = tl & 1u, bph = (tl >> 1) & 1u;
+      // every 4th tile: has the next rung been reached by k documents?  (requested now, consumed after the tile)
+      const bool poll = ladder && (tl & 3u) == 3u && lv + 1 < kLevels;
+      uint32_t polled = 0;
+      if (poll) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(polled) : "l"(my_cnt + lv + 1) : "memory");
       oi_mbar_wait(&s_tfull[b], bph);
       oi_tc_fence_after();
       const uint32_t doc0 = t * p.tile_mul * kTileDocs;
@@ -333,6 +351,12 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
                     if (sc >= thr_s) {
                       const u64 key = oi_make_key(sc, p.doc_base + doc0 + hf * 32 + 8 * g + e);
                       if (key > thr_key) { buf[cnt] = key; ++cnt; }
+                      if (sc >= nxt_s) {  // one more document on the rungs above (ascending: stop at the first it misses)
+                        for (uint32_t j = lv + 1; j < kLevels; ++j) {
+                          if (!(sc >= __ldg(my_lvl + j))) break;
+                          atomicAdd(my_cnt + j, 1u);
+                        }
+                      }
                     }
                   }
                 }
@@ -344,6 +368,12 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
       oi_tc_fence_before();
       __syncwarp();
       if (lane == 0) oi_mbar_arrive(&s_tempty[b]);  // both halves are in registers / consumed: the accumulator may be overwritten
+      if (poll && polled >= p.k) {  // k documents reached the next rung: it bounds the k-th best score from below
+        ++lv;
+        const u64 cand_key = (u64)oi_ord(nxt_s) << 32;
+        if (cand_key > thr_key) { thr_key = cand_key; thr_s = nxt_s; }
+        nxt_s = lv + 1 < kLevels ? __ldg(my_lvl + lv + 1) : INFINITY;
+      }
 
       // a list that could overflow during the next tile is reduced to its best k by the whole warp
       uint32_t mask = __ballot_sync(0xFFFFFFFFu, cnt + kTileDocs > cap);
@@ -415,12 +445,13 @@ struct MergeState {
 };
 
 // One CTA per query: exact top-k over the query's n_ranges candidate lists (+ the sorted list of the
-// earlier passes).  out[q][k] sorted descending; thr_out[q] = k-th key or 0.  The lists are walked as
+// earlier passes).  out[q][k] sorted descending; lvl_thr / lvl_cnt (probe merge only): see the end.  The lists are walked as
 // one flat key sequence (prefix sums of the list lengths in shared memory), a buffer-load at a time,
 // every thread holding up to 8 independent loads in flight.
 constexpr uint32_t kMergeMaxLists = 1020;
 __global__ void __launch_bounds__(256) gemm_merge_kernel(const u64 *cand, const uint32_t *cnts, uint32_t cap, uint32_t n_ranges,
-                                                         uint32_t n_qt, uint32_t k, const u64 *prev, u64 *out, u64 *thr_out) {
+                                                         uint32_t n_qt, uint32_t k, const u64 *prev, u64 *out, float *lvl_thr,
+                                                         uint32_t *lvl_cnt) {
   __shared__ MergeState S;
   __shared__ uint32_t s_pre[kMergeMaxLists + 4];
   __shared__ uint32_t s_wsum[8];
@@ -495,7 +526,16 @@ __global__ void __launch_bounds__(256) gemm_merge_kernel(const u64 *cand, const 
     if (S.cnt > OI_SEL_CAP / 2 || f0 >= total) oi_sel_compact(S.buf, &S.cnt, &S.thr, k, tid, 256, 0);
   }
   for (uint32_t i = tid; i < k; i += 256) out[(size_t)q * k + i] = i < S.cnt ? S.buf[i] : 0ull;
-  if (thr_out && tid == 0) thr_out[q] = (S.cnt == k) ? S.buf[k - 1] : 0ull;
+  // probe merge: the ladder of the main pass.  Rung j = the (k >> j)-th best group maximum: a score (k >> j) / (sample
+  // fraction) documents are expected to reach, valid as a bound once k documents HAVE reached it (counted in the main
+  // pass).  Rung 0 (the k-th best) is valid at once.  Fewer than k group maxima: no bound at all.
+  if (lvl_thr && tid < (int)kLevels) {
+    const uint32_t r = k >> tid;
+    float t = tid == 0 ? -INFINITY : INFINITY;
+    if (S.cnt == k && r >= 1) t = oi_key_score(S.buf[r - 1]);
+    lvl_thr[(size_t)q * kLevels + tid] = t;
+    lvl_cnt[(size_t)q * kLevels + tid] = 0u;
+  }
 }
 
 size_t gemm_smem_bytes(int ring) {
@@ -519,7 +559,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 void oi_gemm_free(oi_index *h) {
   OiGemm *g = h->gemm;
   if (!g) return;
-  cudaFree(g->d_qb); cudaFree(g->d_cand); cudaFree(g->d_cnt); cudaFree(g->d_keys_a); cudaFree(g->d_keys_b); cudaFree(g->d_thr_a);
+  cudaFree(g->d_qb); cudaFree(g->d_cand); cudaFree(g->d_cnt); cudaFree(g->d_keys_a); cudaFree(g->d_keys_b); cudaFree(g->d_lvl_thr); cudaFree(g->d_lvl_cnt);
   delete g;
   h->gemm = nullptr;
 }
@@ -545,7 +585,8 @@ static oi_status gemm_prepare(oi_index *h) {
   GM_CK(cudaMalloc(&g->d_cnt, g->max_lists * sizeof(uint32_t)));
   GM_CK(cudaMalloc(&g->d_keys_a, B * K * sizeof(u64)));
   GM_CK(cudaMalloc(&g->d_keys_b, B * K * sizeof(u64)));
-  GM_CK(cudaMalloc(&g->d_thr_a, B * sizeof(u64)));
+  GM_CK(cudaMalloc(&g->d_lvl_thr, B * kLevels * sizeof(float)));
+  GM_CK(cudaMalloc(&g->d_lvl_cnt, B * kLevels * sizeof(uint32_t)));
 
   void *fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -592,7 +633,7 @@ static oi_status gemm_prepare(oi_index *h) {
 bool oi_gemm_lite_ok(const oi_index *h) { return 12 % (h->desc.dim / kKBlock) == 0; }
 
 static oi_status gemm_launch(oi_index *h, uint32_t nq, uint32_t n_qt, uint32_t n_ranges, uint32_t k, uint32_t cap,
-                             uint32_t tile_begin, uint32_t tile_end, uint32_t tile_mul, bool probe, const u64 *thr_in, float *dump,
+                             uint32_t tile_begin, uint32_t tile_end, uint32_t tile_mul, bool probe, const float *lvl_thr, float *dump,
                              bool lite, cudaStream_t st) {
   OiGemm *g = h->gemm;
   GemmParams p;
@@ -600,7 +641,7 @@ static oi_status gemm_launch(oi_index *h, uint32_t nq, uint32_t n_qt, uint32_t n
   p.n_rows = (uint32_t)h->desc.n_docs; p.dim = h->desc.dim; p.doc_base = (uint32_t)h->desc.doc_base;
   p.k = k; p.nq = nq; p.n_qt = n_qt; p.n_ranges = n_ranges;
   p.tile_begin = tile_begin; p.tile_end = tile_end; p.tile_mul = tile_mul; p.probe = probe ? 1u : 0u;
-  p.thr_in = thr_in; p.cand = g->d_cand; p.cand_cnt = g->d_cnt; p.cap = cap; p.dump = dump;
+  p.lvl_thr = lvl_thr; p.lvl_cnt = g->d_lvl_cnt; p.cand = g->d_cand; p.cand_cnt = g->d_cnt; p.cap = cap; p.dump = dump;
   p.debug = (uint32_t)h->gemm_debug;
   p.tma3d = g->tma3d ? 1u : 0u;
   const uint32_t grid = n_ranges * n_qt;
@@ -644,28 +685,29 @@ oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, u
     ++h->launches;
     GM_CK(cudaGetLastError());
   }
-  // Two passes.  PROBE: every CTA scores `pt` tiles of a strided sample of the shard (about 1/128 of its tiles) and
+  // Two passes.  PROBE: every CTA scores `pt` tiles of a strided sample of the shard (about 1/256 of its tiles) and
   // keeps only the maxima of groups of 8 scores; the merge's k-th best of those is a score at least k documents
-  // reach.  MAIN: all tiles, filtered by that bound (a list that still fills up is cut to its best k in the kernel,
-  // which raises its own bound), then the exact top-k of what passed.  Shards with only a few tiles per CTA skip the
-  // probe: their lists hold everything.
+  // reach, and its k/2-th, k/4-th ... best are the rungs of the ladder.  MAIN: all tiles, filtered by the bound, which
+  // climbs the ladder as the grid-wide counters confirm the rungs (a list that still fills up is cut to its best k in
+  // the kernel, which raises its own bound), then the exact top-k of what passed.  Shards with only a few tiles per
+  // CTA skip the probe: their lists hold everything.
   const uint32_t tiles_per_cta = (n_tiles + n_ranges - 1) / n_ranges;
   const uint32_t pt_max = std::max<uint32_t>(1u, (cap - kTileDocs) / 8u);
-  uint32_t pt = h->gemm_sample_tiles > 0 ? (uint32_t)h->gemm_sample_tiles : (tiles_per_cta + 127) / 128;
+  uint32_t pt = h->gemm_sample_tiles > 0 ? (uint32_t)h->gemm_sample_tiles : (tiles_per_cta + 255) / 256;
   pt = std::min(std::max(pt, 1u), pt_max);
   const bool do_probe = !d_dump && (h->gemm_sample_tiles > 0 || tiles_per_cta >= 8);
-  const u64 *thr = nullptr;
+  const float *thr = nullptr;
   if (do_probe) {
     const uint32_t n_probe = (uint32_t)std::min<uint64_t>((uint64_t)n_ranges * pt, n_tiles);
     const uint32_t stride = n_tiles / n_probe;
     if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_probe, stride, true, nullptr, nullptr, lite, st))) return s;
-    gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, g->d_keys_a, g->d_thr_a);
+    gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, g->d_keys_a, g->d_lvl_thr, g->d_lvl_cnt);
     ++h->launches;
     GM_CK(cudaGetLastError());
-    thr = g->d_thr_a;
+    thr = g->d_lvl_thr;
   }
   if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_tiles, 1, false, thr, d_dump, lite, st))) return s;
-  gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, d_out_keys, nullptr);
+  gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, d_out_keys, nullptr, nullptr);
   ++h->launches;
   GM_CK(cudaGetLastError());
   return OI_OK;

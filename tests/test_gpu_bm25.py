@@ -144,8 +144,12 @@ def test_bm25_edge_cases(oi):
         assert np.array_equal(ids, wi)
         assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
         assert np.all(ids[0] == oi.NO_DOC) and np.all(sc[0] == 0)
+        # more than 64 distinct known terms: the first 64 (first-seen order) are scored (SPEC §3), on both paths
+        ids65, sc65 = ix.search_bm25([list(range(65))], k)
+        assert np.array_equal(ids65[0], ids[4]) and np.array_equal(sc65[0], sc[4])
+        # a call may not carry more raw term ids than the staging array holds (64 x max_batch)
         with pytest.raises(oi.OiError) as e:
-            ix.search_bm25([list(range(65))], k)
+            ix.search_bm25([[1] * (64 * len(queries) + 1)], k)
         assert e.value.status == 1
         # nq == 0 is a no-op
         ids0, _ = ix.search_bm25([], k)

@@ -164,7 +164,7 @@ def test_bm25_many_raw_terms_host_and_dev_paths_agree(oi):
     rng.shuffle(q_dups)
     q_many = rng.permutation(vocab)[:150].astype(np.uint32)                                    # 150 distinct: the first 64 count
     queries = [q_dups, q_many, np.array([3, 3, 3], np.uint32)]
-    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=4) as ix:
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=k, max_batch=8) as ix:
         ix.load_bm25(corp["term_offsets"], corp["doc_ids"], corp["tfs"], corp["doc_len"])
         ix.bm25_finalize()
         ids, sc = ix.search_bm25(queries, k)
