@@ -17,7 +17,12 @@
  *    DomainError::SourceFailure{name:"gpu-search", message} (src/domain/error.rs:17-18).
  *  - calls on one handle may come from many threads at once (the reference awaits ports
  *    concurrently on one &self: src/application/analyze.rs:30-37); the library serialises
- *    them internally.  Calls are blocking.
+ *    them internally (one set of workspaces per handle).  Host-buffer calls are blocking.
+ *    `_dev` calls return after enqueueing; calls enqueued on DIFFERENT streams are ordered on
+ *    the device by the library (an event recorded at the end of every call is waited for by
+ *    the next call's stream), so they never overlap on the shared workspaces.
+ *  - oi_last_error returns a pointer into thread-local storage: valid until the calling
+ *    thread's next oi_last_error call.
  *  - result lists are ordered score-descending, ties by ascending doc id (docs/SPEC.md §1);
  *    short lists are padded with (OI_NO_DOC, 0).  Doc ids are GLOBAL (doc_base + local row).
  *  - there is no CPU fallback: without a CUDA device every call fails with OI_ERR_NO_DEVICE.
@@ -80,7 +85,9 @@ const char *oi_last_error(const oi_index *h);
 const char *oi_version(void);
 
 /* ---- embeddings ---------------------------------------------------------------------------- */
-/* rows [first_doc, first_doc+n) (shard-local numbering), already L2-normalised, in the index dtype */
+/* rows [first_doc, first_doc+n) (shard-local numbering), already L2-normalised, in the index dtype.  Chunks must
+ * extend the loaded prefix or rewrite rows inside it (first_doc <= rows loaded so far): searches are refused until
+ * every row has been loaded, so uninitialised memory is never scored. */
 oi_status oi_index_load_embeddings(oi_index *h, const void *rows, uint64_t first_doc, uint64_t n);
 /* generate this shard's rows on the device (SPEC §9, stream 0, rows doc_base..doc_base+n_docs) */
 oi_status oi_index_synth_embeddings(oi_index *h, uint64_t seed);
@@ -113,7 +120,9 @@ oi_status oi_index_comm_init(oi_index *h, int32_t rank, int32_t world_size,
 /* queries: nq x dim f32, L2-normalised.  out_ids/out_scores: nq x k. */
 oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_t nq, uint32_t k,
                            uint32_t *out_ids, float *out_scores);
-/* query j's term ids are q_terms[q_offsets[j] .. q_offsets[j+1]) (<= 64 terms per query) */
+/* query j's term ids are q_terms[q_offsets[j] .. q_offsets[j+1]): any number of raw ids; duplicates and unknown ids are
+ * dropped and at most the first 64 distinct known terms (first-seen order) are scored (docs/SPEC.md §3).  One call may
+ * carry at most 64 x max_batch ids in total. */
 oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets,
                          uint32_t nq, uint32_t k, uint32_t *out_ids, float *out_scores);
 /* RRF (SPEC §4) of the two global top-k lists; out_rank_* are 1-based, 0 = not in that list */
@@ -147,14 +156,19 @@ oi_status oi_lexicon_analyze(int32_t device, const uint8_t *texts, const uint64_
 uint64_t oi_index_launch_count(const oi_index *h);
 /* named integer knobs: "cosine_variant" (0 = ldg, 1 = bulk-copy pipeline), "cosine_gemm_min_batch"
  * (bf16 batches of at least this many queries take the tcgen05 tensor-core path; 0 = never),
- * "cosine_gemm_cap" / "cosine_gemm_sample_tiles" (tests: force list compaction / the two-pass flow);
+ * "cosine_gemm_cap" (tests: force list compaction), "cosine_gemm_sample_tiles" (probe-pass tiles per CTA; > 0 also forces
+ * the probe pass on small shards);
  * "cosine_multi_query" (2 = default: a call with several queries reads the matrix once per group of 4 queries when a
  * row is at most 1536 bytes, on the bulk-copy pipeline for f32 rows; 1 = same with direct loads; 0 = every query
  * scans the matrix on its own);
  * BM25 schedule: "bm25_warps" (warps per CTA), "bm25_block_docs" (documents per block, power of two >= 1024),
  * "bm25_stage_slots" (TMA-staged 64-posting chunks per warp), "bm25_items_per_warp", "bm25_dense_div" (before
  * finalize: a term in >= n_docs / div documents gets a dense weight column), "bm25_no_cold_bound" (tests);
- * every setting returns the same lists bit for bit.  "comm_debug_skip_gather": timing experiments only. */
+ * every setting returns the same lists bit for bit.
+ * Hybrid call: "hybrid_overlap" (0 = default: the two legs back to back; 1 = BM25 on a second stream next to the
+ * GEMM, co-resident "lite" kernels with "overlap_bm25_warps" / "overlap_bm25_slots"; 2 = SM partition with
+ * "overlap_gemm_sms"): identical results, measured in profiles/r02_overlap_sweep.md.
+ * "cosine_gemm_debug", "cosine_gemm_lite", "comm_debug_skip_gather": timing experiments only. */
 oi_status oi_index_set_option(oi_index *h, const char *name, int64_t value);
 /* tests: the raw nq x n_docs f32 score matrix of the tensor-core path (bf16 index, small shards) */
 oi_status oi_debug_cosine_gemm_scores(oi_index *h, const float *queries, uint32_t nq, float *out_scores);

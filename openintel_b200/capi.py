@@ -33,7 +33,8 @@ class Bm25Params(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libopenintel_gpu.so")
+    # OI_GPU_LIB: A/B experiments against another build of the same C ABI (tools/ only); the product loads the in-tree .so
+    return os.environ.get("OI_GPU_LIB") or os.path.join(_HERE, "libopenintel_gpu.so")
 
 
 _lib = None

@@ -195,6 +195,16 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     oi_cosine_scan_tuning((int)(value >> 8), (int)(value & 255));
     return OI_OK;
   }
+  if (!strcmp(name, "cosine_gemm_pair")) {  // 0: never CTA pairs (every CTA issues its own M = 128 MMAs)
+    OI_REQUIRE(value == 0 || value == 1, "cosine_gemm_pair must be 0 or 1");
+    h->gemm_pair = (int)value;
+    return OI_OK;
+  }
+  if (!strcmp(name, "cosine_gemm_pair_ring")) {
+    OI_REQUIRE(value == 24 || value == 48, "cosine_gemm_pair_ring must be 24 or 48");
+    h->gemm_pair_ring = (int)value;
+    return OI_OK;
+  }
   if (!strcmp(name, "cosine_gemm_lite")) {  // experiments: the stand-alone cosine call runs the 96 KB-ring kernel too
     h->gemm_force_lite = value != 0;
     return OI_OK;
@@ -229,7 +239,7 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     return OI_OK;
   }
   if (!strcmp(name, "cosine_gemm_debug")) {  // timing experiments: results are garbage while it is set
-    OI_REQUIRE(value >= 0 && value <= 7, "cosine_gemm_debug is a 3-bit mask");
+    OI_REQUIRE(value >= 0 && value <= 15, "cosine_gemm_debug is a 4-bit mask");
     h->gemm_debug = (int)value;
     return OI_OK;
   }

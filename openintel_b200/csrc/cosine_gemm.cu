@@ -53,7 +53,9 @@ struct OiGemm {
   uint32_t cap = 0;
   size_t max_lists = 0;
   CUtensorMap tmap;
+  CUtensorMap tmap_pair;          // the same 3-D view with 32-row boxes (CTA pairs: each CTA loads half a tile)
   bool tma3d = false;
+  bool pair_ok = false;
   bool ready = false;
 };
 
@@ -81,7 +83,8 @@ struct GemmParams {
   uint32_t cap;
   float *dump;                    // tests: [nq][n_rows] raw scores, or nullptr
   uint32_t tma3d;                 // the tensor map is the 3-D (k-block-major) view: one TMA op per stage
-  uint32_t debug;                 // timing experiments: bit 0 = no MMA issue, bit 1 = no TMA loads, bit 2 = no score filter (results are garbage)
+  uint32_t debug;                 // timing experiments: bit 0 = no MMA issue, bit 1 = no TMA loads, bit 2 = no score filter (results are garbage),
+                                  // bit 3 = the ladder stays on rung 0 (results stay exact)
 };
 
 __device__ __forceinline__ void warp_bitonic_desc(u64 *buf, uint32_t n, int lane) {
@@ -113,22 +116,64 @@ __device__ __forceinline__ u64 warp_compact_list(u64 *list, uint32_t n, uint32_t
   return thr;
 }
 
+// Slow path of the epilogue filter, OUT OF LINE on purpose: eight consecutive scores of one query (a group whose maximum
+// passed the filter in some lane of the warp) are tested one by one and the survivors appended to the lane's candidate
+// list; survivors that also reach the next rung of the threshold ladder are counted grid-wide.  Inlined and unrolled
+// over the 64 scores of a tile this code was 15 KB per kernel: whenever survivors were frequent it evicted the MMA
+// and TMA loops from the instruction cache (ncu: 9.5 "no instruction" stall cycles per issue, tensor pipe 13 % active)
+// and a tile with a survivor cost the whole SM thousands of cycles.  Returns the new list length.
+__device__ __noinline__ uint32_t gemm_open_group(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t s4, uint32_t s5,
+                                                 uint32_t s6, uint32_t s7, u64 *buf, uint32_t cnt, float thr_s, u64 thr_key,
+                                                 uint32_t doc, uint32_t doc_end, float nxt_s, const float *lvl, uint32_t *lvl_cnt,
+                                                 uint32_t lv) {
+  const uint32_t sv[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float sc = __uint_as_float(sv[e]);
+    const u64 key = oi_make_key(sc, doc + e);
+    const bool in_range = doc + e < doc_end;  // rows past the end of the shard are zero-filled by the TMA unit
+    const bool ok = in_range && sc >= thr_s && key > thr_key;
+    if (ok) buf[cnt] = key;
+    cnt += ok ? 1u : 0u;
+    if (in_range && sc >= nxt_s) {  // one more document on the rungs above (ascending: stop at the first it misses)
+      for (uint32_t j = lv + 1; j < 8u; ++j) {
+        if (!(sc >= __ldg(lvl + j))) break;
+        atomicAdd(lvl_cnt + j, 1u);
+      }
+    }
+  }
+  return cnt;
+}
+
+// tests only (oi_debug_cosine_gemm_scores): eight raw scores of one query go to the dump matrix; out of line for the
+// same code-size reason
+__device__ __noinline__ void gemm_dump_group(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t s4, uint32_t s5, uint32_t s6,
+                                             uint32_t s7, float *dst, uint32_t n) {
+  const uint32_t sv[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if ((uint32_t)e < n) dst[e] = __uint_as_float(sv[e]);
+}
+
 // Ring geometry for a row of NKB k-blocks (dim = 64 * NKB): the 192 KB ring holds 24 slabs of
 // 64 rows x 128 B.  A stage = KBS slabs (one TMA op, one mbarrier); a tile = SPT stages; the ring
 // holds TIF whole tiles, so inside a group of TIF tiles every stage index is a compile-time constant.
 // RING = slabs in the ring: 24 (192 KB, the stand-alone kernel) or 12 (96 KB, the "lite" kernel that shares an SM
 // with a BM25 CTA when the hybrid call overlaps its two legs).
-template <int NKB, int RING>
+// CG2 (CTA pairs): a slab holds this CTA's 32 of the tile's 64 rows (4 KB); the peer CTA holds the other 32.
+template <int NKB, int RING, bool CG2 = false>
 struct GemmShape {
   static_assert(RING % NKB == 0, "dim / 64 must divide the ring");
   static constexpr int KBS = (NKB % 4 == 0) ? 4 : (NKB % 2 == 0) ? 2 : 1;
   static constexpr int SPT = NKB / KBS;
   static constexpr int TIF = RING / NKB;
   static constexpr int STAGES = SPT * TIF;
-  static constexpr uint32_t STAGE_BYTES = KBS * 8192u;
-  static constexpr uint32_t RING_BYTES = RING * 8192u;
+  static constexpr uint32_t SLAB_BYTES = CG2 ? 4096u : 8192u;
+  static constexpr uint32_t STAGE_BYTES = KBS * SLAB_BYTES;
+  static constexpr uint32_t RING_BYTES = RING * SLAB_BYTES;
 };
 constexpr uint32_t kMaxStages = 24;
+static_assert(true, "");
 
 __device__ __forceinline__ uint32_t oi_elect_one() {
   uint32_t pred;
@@ -142,9 +187,15 @@ __device__ __forceinline__ uint32_t oi_elect_one() {
   return pred;
 }
 
-template <int NKB, int RING>
+// CG2: the kernel runs as clusters of two CTAs (the two SMs of a TPC).  CTA `rank` of a pair owns query tile
+// 2 * (pair % (n_qt / 2)) + rank and HALF of every document tile (rows 32 * rank .. 32 * rank + 31); the leader (rank 0)
+// issues ONE tcgen05.mma.cta_group::2 of M = 256 per k-step for both.  Every document row then enters exactly one SM
+// (L2 -> SM traffic = the algorithmic bytes instead of twice that) and every SM reads half the B operand per flop from
+// its shared memory (at M = 128, N = 64 the B reads plus the TMA writes used ~90 % of the shared-memory bandwidth and
+// held the tensor pipe at 80 %: profiles/r02_ncu_cosine_gemm.md).
+template <int NKB, int RING, bool EARLY, bool CG2 = false>
 __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const GemmParams &p) {
-  using Sh = GemmShape<NKB, RING>;
+  using Sh = GemmShape<NKB, RING, CG2>;
   constexpr int KBS = Sh::KBS, SPT = Sh::SPT, TIF = Sh::TIF, STAGES = Sh::STAGES;
   extern __shared__ unsigned char s_raw[];
   unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
@@ -158,18 +209,22 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_qready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.x = range * n_qt + qt in both layouts (a pair = two consecutive CTAs = two consecutive query tiles)
   const uint32_t qt = blockIdx.x % p.n_qt, range = blockIdx.x / p.n_qt;
   const uint32_t t0 = p.tile_begin + range;
+  const uint32_t rank = CG2 ? oi_cluster_ctarank() : 0u;  // == qt & 1
 
   if (threadIdx.x == 0) {
+    // CG2: full / tempty / qready are used in the LEADER only (both CTAs' copies report to it / arrive on it),
+    // empty / tfull in each CTA (the leader's commits arrive on both)
     for (int s = 0; s < STAGES; ++s) { oi_mbar_init(&s_full[s], 1); oi_mbar_init(&s_empty[s], 1); }
-    for (uint32_t b = 0; b < 2; ++b) { oi_mbar_init(&s_tfull[b], 1); oi_mbar_init(&s_tempty[b], 4); }
-    oi_mbar_init(s_qready, 128);
+    for (uint32_t b = 0; b < 2; ++b) { oi_mbar_init(&s_tfull[b], 1); oi_mbar_init(&s_tempty[b], CG2 ? 8 : 4); }
+    oi_mbar_init(s_qready, CG2 ? 256 : 128);
     oi_mbar_fence_init();
   }
-  if (warp == 1) oi_tmem_alloc(s_tmem, kTmemCols);
+  if (warp == 1) { if (CG2) oi_tmem_alloc2(s_tmem, kTmemCols); else oi_tmem_alloc(s_tmem, kTmemCols); }
   oi_tc_fence_before();
-  __syncthreads();
+  if (CG2) oi_cluster_sync(); else __syncthreads();  // the peer's barriers exist before anything is signalled to them
   oi_tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
@@ -192,7 +247,14 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
           const int s = u * SPT + j;
           oi_mbar_wait(&s_empty[s], ph ^ 1u);
           if (leader) {
-            if (p.debug & 2u) {
+            if (CG2) {
+              // each CTA brings its 32 rows of the tile; both report their bytes to the leader CTA's barrier, which
+              // expects the two halves (a half that lands before the expectation is posted only makes the count
+              // negative for a while: the phase cannot complete before the leader's own arrival)
+              if (rank == 0) oi_mbar_expect_tx(&s_full[s], 2u * Sh::STAGE_BYTES);
+              oi_tma_load_3d_pair(s_stage + (size_t)s * Sh::STAGE_BYTES, &tmap, 0, (int32_t)(t * p.tile_mul * kTileDocs + rank * 32u), j * KBS,
+                                  &s_full[s]);
+            } else if (p.debug & 2u) {
               oi_mbar_arrive(&s_full[s]);
             } else {
               oi_mbar_expect_tx(&s_full[s], Sh::STAGE_BYTES);
@@ -210,12 +272,13 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------- MMA issuer ---------------------------------------------------
+  } else if (warp == 1 && (!CG2 || rank == 0)) {
+    // ------------------------------- MMA issuer (CG2: in the leader CTA only) ----------------------
     const bool leader = oi_elect_one();
-    constexpr uint32_t idesc = oi_umma_idesc_bf16(128, kTileDocs);
+    constexpr uint32_t idesc = oi_umma_idesc_bf16(CG2 ? 256 : 128, kTileDocs);
+    constexpr uint32_t kSlab16 = Sh::SLAB_BYTES / 16;  // descriptor address units per slab
     const uint64_t desc0 = oi_umma_smem_desc_sw128(oi_smem_u32(s_stage));
-    oi_mbar_wait(s_qready, 0);
+    if (CG2) oi_mbar_wait_cluster(s_qready, 0); else oi_mbar_wait(s_qready, 0);
     oi_tc_fence_after();
     uint32_t grp = 0, tl = 0;
     for (uint32_t tb = t0; tb < p.tile_end; tb += TIF * p.n_ranges, ++grp) {
@@ -226,7 +289,7 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
         if (t >= p.tile_end) break;
         const uint32_t b = tl & 1u, bph = (tl >> 1) & 1u;
         ++tl;
-        oi_mbar_wait(&s_tempty[b], bph ^ 1u);
+        if (CG2) oi_mbar_wait_cluster(&s_tempty[b], bph ^ 1u); else oi_mbar_wait(&s_tempty[b], bph ^ 1u);
         oi_tc_fence_after();
         const uint32_t d_addr = tmem + kDCol0 + b * kTileDocs;
 #pragma unroll
@@ -235,7 +298,7 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
           oi_mbar_wait(&s_full[s], ph);
           oi_tc_fence_after();
           if (leader) {
-            if (p.debug & 1u) {
+            if (!CG2 && (p.debug & 1u)) {
               oi_mbar_arrive(&s_empty[s]);
               if (j == SPT - 1) oi_mbar_arrive(&s_tfull[b]);
             } else {
@@ -245,18 +308,20 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
                 for (int ks = 0; ks < 4; ++ks) {
                   // A: 16 bf16 of K = 8 TMEM columns; B: slab (s * KBS + kk), 32 B per k-step inside the swizzle atom
                   const int kbi = j * KBS + kk;
-                  oi_umma_ts_bf16(d_addr, tmem + (uint32_t)((kbi * 4 + ks) * 8), desc0 + (uint64_t)((s * KBS + kk) * 512 + ks * 2), idesc,
-                                  (kbi | ks) != 0 ? 1u : 0u);
+                  const uint64_t db = desc0 + (uint64_t)((s * KBS + kk) * kSlab16 + ks * 2);
+                  if (CG2) oi_umma2_ts_bf16(d_addr, tmem + (uint32_t)((kbi * 4 + ks) * 8), db, idesc, (kbi | ks) != 0 ? 1u : 0u);
+                  else oi_umma_ts_bf16(d_addr, tmem + (uint32_t)((kbi * 4 + ks) * 8), db, idesc, (kbi | ks) != 0 ? 1u : 0u);
                 }
               }
-              oi_umma_commit(&s_empty[s]);  // the stage is free once these MMAs have read it
-              if (j == SPT - 1) oi_umma_commit(&s_tfull[b]);
+              // the stage is free (in both CTAs) once these MMAs have read it; the accumulator is ready in both
+              if (CG2) oi_umma2_commit_mc(&s_empty[s], 3u); else oi_umma_commit(&s_empty[s]);
+              if (j == SPT - 1) { if (CG2) oi_umma2_commit_mc(&s_tfull[b], 3u); else oi_umma_commit(&s_tfull[b]); }
             }
           }
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ------------------------------- epilogue: one thread per query -------------------------------
     const uint32_t quarter = (uint32_t)warp & 3u;  // TMEM lanes this warp may touch: 32 * (warp % 4)
     const uint32_t row = quarter * 32 + lane;
@@ -266,7 +331,8 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
       // warp is 4 KB contiguous, 128 B per lane
       const uint32_t n_chunks = p.dim / 64;
       const uint4 *qsrc = reinterpret_cast<const uint4 *>(p.qb) + ((size_t)(qt * 4 + quarter) * n_chunks * 32 + lane) * 8;
-      for (uint32_t ch = 0; ch < n_chunks; ++ch) {  // once per launch: no prefetch, 32 live registers
+#pragma unroll 1
+      for (uint32_t ch = 0; ch < n_chunks; ++ch) {  // once per launch: no prefetch, no unrolling (code size)
         uint32_t r[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -277,7 +343,7 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
       }
       oi_tmem_wait_st();
       oi_tc_fence_before();
-      oi_mbar_arrive(s_qready);
+      if (CG2) oi_mbar_arrive_cluster(s_qready, 0u); else oi_mbar_arrive(s_qready);
     }
     const uint32_t q = qt * 128 + row;
     const bool qv = q < p.nq;
@@ -291,7 +357,8 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
     const float *my_lvl = p.lvl_thr + (size_t)(qv ? q : 0) * kLevels;
     uint32_t *my_cnt = p.lvl_cnt + (size_t)(qv ? q : 0) * kLevels;
     uint32_t lv = 0;
-    float thr_s = ladder ? __ldg(my_lvl) : -INFINITY;
+    const bool climb = ladder && !(p.debug & 8u);
+    float thr_s = ladder ? __ldg(my_lvl) : (qv ? -INFINITY : INFINITY);  // lanes without a query never pass the filter
     float nxt_s = ladder ? __ldg(my_lvl + 1) : INFINITY;  // the rung being counted
     u64 thr_key = (ladder && thr_s > -INFINITY) ? ((u64)oi_ord(thr_s) << 32) : 0ull;
 
@@ -299,75 +366,76 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
     for (uint32_t t = t0; t < p.tile_end; t += p.n_ranges, ++tl) {
       const uint32_t b = tl & 1u, bph = (tl >> 1) & 1u;
       // every 4th tile: has the next rung been reached by k documents?  (requested now, consumed after the tile)
-      const bool poll = ladder && (tl & 3u) == 3u && lv + 1 < kLevels;
+      const bool poll = climb && (tl & 3u) == 3u && lv + 1 < kLevels;
       uint32_t polled = 0;
       if (poll) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(polled) : "l"(my_cnt + lv + 1) : "memory");
       oi_mbar_wait(&s_tfull[b], bph);
       oi_tc_fence_after();
       const uint32_t doc0 = t * p.tile_mul * kTileDocs;
       const uint32_t n_valid = min(kTileDocs, p.n_rows - doc0);
-      // the 64 scores of the tile are taken in two halves of 32 columns (32 live registers instead of 64: the kernel
-      // stays below 128 registers per thread, so a BM25 CTA fits next to it on the SM)
+      // NH = 1 (stand-alone kernel): all 64 scores of the tile are pulled at once and the accumulator is released as
+      // soon as they are in registers -- the MMAs of tile t + 2 never wait for this warp's arithmetic (holding the
+      // accumulator through two TMEM round trips and the filter cost 30 % of the kernel: profiles/r02_gemm_notes.md).
+      // NH = 2 (lite kernel, 128 registers): two halves of 32 columns, released after the second.
+      constexpr int NH = EARLY ? 1 : 2, W = 64 / NH;
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t v[32];
-        oi_tmem_ld32(lane_taddr + kDCol0 + b * kTileDocs + hf * 32, v);
+      for (int hf = 0; hf < NH; ++hf) {
+        uint32_t v[W];
+        oi_tmem_ld32(lane_taddr + kDCol0 + b * kTileDocs + hf * W, v);
+        if (EARLY) oi_tmem_ld32(lane_taddr + kDCol0 + b * kTileDocs + 32, v + (EARLY ? 32 : 0));
         oi_tmem_wait_ld();
-        if (n_valid < kTileDocs) {  // last tile of the shard: columns past the end never qualify
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if ((uint32_t)(hf * 32 + i) >= n_valid) v[i] = 0x7FC00000u;  // NaN: loses every fmaxf and every >= compare
+        if (EARLY || hf == NH - 1) {
+          oi_tc_fence_before();
+          __syncwarp();
+          // the scores are in registers: the accumulator may be overwritten (CG2: the leader's issuer waits for both CTAs)
+          if (lane == 0) { if (CG2) oi_mbar_arrive_cluster(&s_tempty[b], 0u); else oi_mbar_arrive(&s_tempty[b]); }
         }
-        if (qv && !(p.debug & 4u)) {
-          if (p.dump) {
+        if (p.dump) {  // warp-uniform
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if ((uint32_t)(hf * 32 + i) < n_valid) p.dump[(size_t)q * p.n_rows + doc0 + hf * 32 + i] = __uint_as_float(v[i]);
+          for (int g = 0; g < W / 8; ++g) {
+            const uint32_t c0 = (uint32_t)(hf * W + 8 * g);
+            gemm_dump_group(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7],
+                            p.dump + (size_t)(qv ? q : 0) * p.n_rows + doc0 + c0, (qv && n_valid > c0) ? n_valid - c0 : 0u);
           }
-          // two-level filter: maxima of 4 groups of 8 scores, then their maximum.  Most tiles stop at the single
-          // compare; a tile with a survivor only opens the groups that hold one.
-          float gm[4];
+        }
+        // two-level filter: maxima of groups of 8 scores, then their maximum.  Most tiles stop at the single compare.
+        // Every branch below is WARP-UNIFORM (ballots) and the per-score work inside an opened group is predicated: the
+        // first version branched per lane and per score, 64 divergent regions per tile, and a tile with a survivor cost
+        // the warp more than a thousand cycles (profiles/r02_gemm_notes.md).  Lanes without a query carry thr_s = +inf.
+        constexpr int NG = W / 8;
+        float gm[NG];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float a = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
-            const float c = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
-            gm[g] = fmaxf(fmaxf(a, c), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+        for (int g = 0; g < NG; ++g) {
+          const float a = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+          const float c = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
+          gm[g] = fmaxf(fmaxf(a, c), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+        }
+        if (p.probe) {
+          // probe pass: a group maximum is the score of one real document and the groups are disjoint, so the k-th
+          // largest of them is a score at least k documents reach.  Score-only keys (doc field 0).
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            // a partial last tile is left out of the sample: its zero-filled columns are not documents
+            const bool ok = qv && n_valid == kTileDocs;
+            if (ok) buf[cnt] = (u64)oi_ord(gm[g]) << 32;
+            cnt += ok ? 1u : 0u;
           }
-          if (p.probe) {
-            // probe pass: a group maximum is the score of one real document and the groups are disjoint, so the k-th
-            // largest of them is a score at least k documents reach.  Score-only keys (doc field 0).
+        } else if (!(p.debug & 4u)) {
+          float m = gm[0];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (gm[g] == gm[g]) { buf[cnt] = (u64)oi_ord(gm[g]) << 32; ++cnt; }  // NaN = a group past the end of the shard
-          } else {
-            const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-            if (m >= thr_s) {
+          for (int g = 1; g < NG; ++g) m = fmaxf(m, gm[g]);
+          if (__any_sync(0xFFFFFFFFu, m >= thr_s)) {
+            const float cnt_s = climb ? nxt_s : INFINITY;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (gm[g] >= thr_s) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float sc = __uint_as_float(v[8 * g + e]);
-                    if (sc >= thr_s) {
-                      const u64 key = oi_make_key(sc, p.doc_base + doc0 + hf * 32 + 8 * g + e);
-                      if (key > thr_key) { buf[cnt] = key; ++cnt; }
-                      if (sc >= nxt_s) {  // one more document on the rungs above (ascending: stop at the first it misses)
-                        for (uint32_t j = lv + 1; j < kLevels; ++j) {
-                          if (!(sc >= __ldg(my_lvl + j))) break;
-                          atomicAdd(my_cnt + j, 1u);
-                        }
-                      }
-                    }
-                  }
-                }
-              }
+            for (int g = 0; g < NG; ++g) {
+              if (__any_sync(0xFFFFFFFFu, gm[g] >= thr_s))
+                cnt = gemm_open_group(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5], v[8 * g + 6],
+                                      v[8 * g + 7], buf, cnt, thr_s, thr_key, p.doc_base + doc0 + hf * W + 8 * g, p.doc_base + p.n_rows,
+                                      cnt_s, my_lvl, my_cnt, lv);
             }
           }
         }
       }
-      oi_tc_fence_before();
-      __syncwarp();
-      if (lane == 0) oi_mbar_arrive(&s_tempty[b]);  // both halves are in registers / consumed: the accumulator may be overwritten
       if (poll && polled >= p.k) {  // k documents reached the next rung: it bounds the k-th best score from below
         ++lv;
         const u64 cand_key = (u64)oi_ord(nxt_s) << 32;
@@ -394,10 +462,10 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
   }
 
   oi_tc_fence_before();
-  __syncthreads();
+  if (CG2) oi_cluster_sync(); else __syncthreads();  // CG2: no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     oi_tc_fence_after();
-    oi_tmem_dealloc(tmem, kTmemCols);
+    if (CG2) oi_tmem_dealloc2(tmem, kTmemCols); else oi_tmem_dealloc(tmem, kTmemCols);
   }
 }
 
@@ -407,12 +475,17 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
 template <int NKB, int RING>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     cosine_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
-  cosine_gemm_body<NKB, RING>(tmap, p);
+  cosine_gemm_body<NKB, RING, true>(tmap, p);
+}
+template <int NKB, int RING>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+    cosine_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+  cosine_gemm_body<NKB, RING, true, true>(tmap, p);
 }
 template <int NKB, int RING>
 __global__ void __maxnreg__(128)
     cosine_gemm_lite_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
-  cosine_gemm_body<NKB, RING>(tmap, p);
+  cosine_gemm_body<NKB, RING, false>(tmap, p);
 }
 
 // f32 queries -> bf16 pairs (RNE, SPEC §2), zero rows up to a multiple of 128, stored in the order the
@@ -538,8 +611,8 @@ __global__ void __launch_bounds__(256) gemm_merge_kernel(const u64 *cand, const 
   }
 }
 
-size_t gemm_smem_bytes(int ring) {
-  return 1024 + (size_t)ring * 8192 + 4 * kCapMax * sizeof(u64) + (2 * kMaxStages + 5) * sizeof(u64) + 16;
+size_t gemm_smem_bytes(int ring, bool pair = false) {
+  return 1024 + (size_t)ring * (pair ? 4096 : 8192) + 4 * kCapMax * sizeof(u64) + (2 * kMaxStages + 5) * sizeof(u64) + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -605,6 +678,13 @@ static oi_status gemm_prepare(oi_index *h) {
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     g->tma3d = cr == CUDA_SUCCESS;
+    if (g->tma3d) {
+      const cuuint32_t box2[3] = {kKBlock, kTileDocs / 2, kbs};
+      cr = ((EncodeTiledFn)fn)(&g->tmap_pair, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, h->d_emb, gdim, gstride, box2, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      g->pair_ok = cr == CUDA_SUCCESS;
+    }
   }
   if (!g->tma3d || h->gemm_force_2d) {
     const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)h->desc.n_docs};
@@ -624,6 +704,13 @@ static oi_status gemm_prepare(oi_index *h) {
   OI_GEMM_ATTR(cosine_gemm_lite_kernel, 1, 12, smem_lite); OI_GEMM_ATTR(cosine_gemm_lite_kernel, 2, 12, smem_lite);
   OI_GEMM_ATTR(cosine_gemm_lite_kernel, 3, 12, smem_lite); OI_GEMM_ATTR(cosine_gemm_lite_kernel, 4, 12, smem_lite);
   OI_GEMM_ATTR(cosine_gemm_lite_kernel, 6, 12, smem_lite); OI_GEMM_ATTR(cosine_gemm_lite_kernel, 12, 12, smem_lite);
+  {
+    const int smem_p24 = (int)gemm_smem_bytes(24, true), smem_p48 = (int)gemm_smem_bytes(48, true);
+    OI_GEMM_ATTR(cosine_gemm_pair_kernel, 1, 24, smem_p24); OI_GEMM_ATTR(cosine_gemm_pair_kernel, 2, 24, smem_p24);
+    OI_GEMM_ATTR(cosine_gemm_pair_kernel, 3, 24, smem_p24); OI_GEMM_ATTR(cosine_gemm_pair_kernel, 4, 24, smem_p24);
+    OI_GEMM_ATTR(cosine_gemm_pair_kernel, 6, 24, smem_p24); OI_GEMM_ATTR(cosine_gemm_pair_kernel, 8, 24, smem_p24);
+    OI_GEMM_ATTR(cosine_gemm_pair_kernel, 12, 24, smem_p24); OI_GEMM_ATTR(cosine_gemm_pair_kernel, 12, 48, smem_p48);
+  }
 #undef OI_GEMM_ATTR
   g->ready = true;
   return OI_OK;
@@ -634,7 +721,7 @@ bool oi_gemm_lite_ok(const oi_index *h) { return 12 % (h->desc.dim / kKBlock) ==
 
 static oi_status gemm_launch(oi_index *h, uint32_t nq, uint32_t n_qt, uint32_t n_ranges, uint32_t k, uint32_t cap,
                              uint32_t tile_begin, uint32_t tile_end, uint32_t tile_mul, bool probe, const float *lvl_thr, float *dump,
-                             bool lite, cudaStream_t st) {
+                             bool lite, bool pair, cudaStream_t st) {
   OiGemm *g = h->gemm;
   GemmParams p;
   p.qb = g->d_qb;
@@ -647,6 +734,24 @@ static oi_status gemm_launch(oi_index *h, uint32_t nq, uint32_t n_qt, uint32_t n
   const uint32_t grid = n_ranges * n_qt;
   const uint32_t nkb = h->desc.dim / kKBlock;
   if (lite && 12 % nkb != 0) lite = false;
+  if (pair) {  // CTA pairs: clusters of two, tcgen05.mma.cta_group::2
+    p.tma3d = 1u;
+    const bool deep = nkb == 12 && h->gemm_pair_ring == 48;
+    const size_t smem_p = gemm_smem_bytes(deep ? 48 : 24, true);
+#define OI_GEMM_PAIR(NKB) case NKB: cosine_gemm_pair_kernel<NKB, 24><<<grid, kGemmThreads, smem_p, st>>>(g->tmap_pair, p); break;
+    if (deep) {
+      cosine_gemm_pair_kernel<12, 48><<<grid, kGemmThreads, smem_p, st>>>(g->tmap_pair, p);
+    } else {
+      switch (nkb) {
+        OI_GEMM_PAIR(1) OI_GEMM_PAIR(2) OI_GEMM_PAIR(3) OI_GEMM_PAIR(4) OI_GEMM_PAIR(6) OI_GEMM_PAIR(8) OI_GEMM_PAIR(12)
+        default: return h->fail(OI_ERR_UNSUPPORTED, "internal: dim %u has no tensor-core kernel", h->desc.dim);
+      }
+    }
+#undef OI_GEMM_PAIR
+    ++h->launches;
+    GM_CK(cudaGetLastError());
+    return OI_OK;
+  }
   const size_t smem = gemm_smem_bytes(lite ? 12 : 24);
 #define OI_GEMM_GO(NKB)                                                                       \
   case NKB:                                                                                   \
@@ -670,7 +775,11 @@ oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, u
   if (s) return s;
   OiGemm *g = h->gemm;
   const uint32_t n_qt = (nq + 127) / 128;
-  const uint32_t ctas = max_ctas ? std::min<uint32_t>(max_ctas, (uint32_t)h->num_sms) : (uint32_t)h->num_sms;
+  // an even number of query tiles runs as CTA pairs (one cta_group::2 MMA of M = 256 per pair); the grid stays
+  // range-major, so two consecutive CTAs (one cluster) are the two query tiles of one pair
+  const bool pair = h->gemm_pair != 0 && g->pair_ok && !lite && n_qt % 2 == 0;
+  uint32_t ctas = max_ctas ? std::min<uint32_t>(max_ctas, (uint32_t)h->num_sms) : (uint32_t)h->num_sms;
+  if (pair) ctas &= ~1u;
   uint32_t n_ranges = ctas / n_qt;
   if (n_ranges < 1) n_ranges = 1;
   const uint32_t n_tiles = (uint32_t)((h->desc.n_docs + kTileDocs - 1) / kTileDocs);
@@ -700,13 +809,13 @@ oi_status oi_gemm_local_keys(oi_index *h, const float *d_queries, uint32_t nq, u
   if (do_probe) {
     const uint32_t n_probe = (uint32_t)std::min<uint64_t>((uint64_t)n_ranges * pt, n_tiles);
     const uint32_t stride = n_tiles / n_probe;
-    if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_probe, stride, true, nullptr, nullptr, lite, st))) return s;
+    if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_probe, stride, true, nullptr, nullptr, lite, pair, st))) return s;
     gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, g->d_keys_a, g->d_lvl_thr, g->d_lvl_cnt);
     ++h->launches;
     GM_CK(cudaGetLastError());
     thr = g->d_lvl_thr;
   }
-  if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_tiles, 1, false, thr, d_dump, lite, st))) return s;
+  if ((s = gemm_launch(h, nq, n_qt, n_ranges, k, cap, 0, n_tiles, 1, false, thr, d_dump, lite, pair, st))) return s;
   gemm_merge_kernel<<<nq, 256, 0, st>>>(g->d_cand, g->d_cnt, cap, n_ranges, n_qt, k, nullptr, d_out_keys, nullptr, nullptr);
   ++h->launches;
   GM_CK(cudaGetLastError());

@@ -106,3 +106,83 @@ __device__ __forceinline__ void oi_tma_load_3d(void *smem_dst, const CUtensorMap
       "l"(m), "r"(oi_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC issue ONE MMA of M = 256 ---------------
+// Each CTA holds its 128 rows of A (tensor memory) and of D, and HALF of B's rows (N / 2) in its shared memory; the
+// leader CTA (cluster rank 0) issues the instruction for both.
+__device__ __forceinline__ uint32_t oi_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void oi_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// whole-warp calls, executed by the same warp of BOTH CTAs of the pair
+__device__ __forceinline__ void oi_tmem_alloc2(uint32_t *smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oi_smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void oi_tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, both CTAs] (+)= A[tmem, both CTAs] * B[smem halves of both CTAs]^T : one thread of the leader CTA issues
+__device__ __forceinline__ void oi_umma2_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one arrival on the mbarrier at this shared-memory offset in EVERY CTA of `cta_mask` when the MMAs issued so far complete
+__device__ __forceinline__ void oi_umma2_commit_mc(void *bar, uint32_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b16 m;\n\t"
+      "cvt.u16.u32 m, %1;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+      "}" ::"r"(oi_smem_u32(bar)),
+      "r"(cta_mask)
+      : "memory");
+}
+// 3-D TMA box into this CTA's shared memory; the transaction bytes are reported to the mbarrier at the same offset in
+// the LEADER CTA of the pair (the cluster-window address with the peer bit cleared)
+__device__ __forceinline__ void oi_tma_load_3d_pair(void *smem_dst, const CUtensorMap *m, int32_t c0, int32_t c1, int32_t c2, void *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          oi_smem_u32(smem_dst)),
+      "l"(m), "r"(oi_smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void oi_mbar_arrive_cluster(void *bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(oi_smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// wait that also acquires at cluster scope (the arrivals come from the peer CTA)
+__device__ __forceinline__ void oi_mbar_wait_cluster(void *bar, uint32_t parity) {
+  uint32_t a = oi_smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE_C;\n\t"
+      "bra WAIT_LOOP_C;\n\t"
+      "WAIT_DONE_C:\n\t"
+      "}" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}

@@ -176,12 +176,13 @@ class IndexBuilder {
     auto it = std::lower_bound(vocab_.begin(), vocab_.end(), token, [](const std::string &a, std::string_view b) { return std::string_view(a) < b; });
     return (it != vocab_.end() && std::string_view(*it) == token) ? (uint32_t)(it - vocab_.begin()) : OI_NO_DOC;
   }
-  // query text -> term ids (unknown tokens dropped, duplicates kept: the scorer counts a term once)
+  // query text -> term ids: unknown tokens dropped, duplicates dropped in first-seen order (SPEC §3 counts a term once
+  // and scores at most the first 64 DISTINCT known terms; the library de-duplicates too, this keeps the arrays small)
   std::vector<uint32_t> query_terms(std::string_view text) const {
     std::vector<uint32_t> out;
     tokenize(text, [&](std::string_view t) {
       const uint32_t id = term_id(t);
-      if (id != OI_NO_DOC) out.push_back(id);
+      if (id != OI_NO_DOC && std::find(out.begin(), out.end(), id) == out.end()) out.push_back(id);
     });
     return out;
   }

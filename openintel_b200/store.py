@@ -48,6 +48,11 @@ class InvalidPostText(ValueError):
 _WHITE_SPACE = "\t\n\x0b\x0c\r \x85\xa0\u1680\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a\u2028\u2029\u202f\u205f\u3000"
 
 
+def _dedupe(ids):
+    """first-seen-order de-duplication of a query's term ids (the 64-term limit counts distinct terms)"""
+    return np.array(list(dict.fromkeys(int(t) for t in ids)), dtype=np.uint32)
+
+
 def parse_post_text(raw):
     """PostText::parse (social_post.rs:13-23): Unicode-whitespace trim, reject empty and > 10 000 chars."""
     t = raw.strip(_WHITE_SPACE)
@@ -189,7 +194,8 @@ class StoreIndex:
             raise
 
     def query_terms(self, texts):
-        return [self.builder.query_terms(t) for t in texts]
+        """term ids of each query text: unknown tokens dropped, duplicates dropped in first-seen order (SPEC §3)"""
+        return [_dedupe(self.builder.query_terms(t)) for t in texts]
 
     def search(self, texts, vectors, k, rrf_k=60):
         q = normalise_rows_f32(np.asarray(vectors, dtype=np.float32).reshape(len(texts), self.dim))
@@ -312,7 +318,7 @@ class ShardedStoreIndex:
             raise
 
     def query_terms(self, texts):
-        return [np.array([self.term_id[t] for t in hostlib.tokenize(x) if t in self.term_id], dtype=np.uint32) for x in texts]
+        return [_dedupe([self.term_id[t] for t in hostlib.tokenize(x) if t in self.term_id]) for x in texts]
 
     def search(self, texts, vectors, k, rrf_k=60):
         q = normalise_rows_f32(np.asarray(vectors, dtype=np.float32).reshape(len(texts), self.dim))

@@ -41,6 +41,33 @@ def test_rust_sys_crate_declares_every_symbol():
         assert ("fn %s(" % s) in rs, "rust -sys crate lacks " + s
 
 
+def test_rust_sources_only_name_symbols_the_header_exports():
+    """the port / adapter / use case / MCP tool / CLI sources under rust/openintel-gpu are uncompiled here: every
+    `sys::oi_*` function, constant and type they name must exist in the header (functions) or in the -sys crate"""
+    sys_rs = open(os.path.join(ROOT, "rust", "openintel-gpu-sys", "src", "lib.rs")).read()
+    declared = set(_declared_symbols())
+    src_dir = os.path.join(ROOT, "rust", "openintel-gpu", "src")
+    files = sorted(f for f in os.listdir(src_dir) if f.endswith(".rs"))
+    assert {"lib.rs", "ports.rs", "adapter.rs", "index_builder.rs", "application_search.rs", "mcp_search.rs", "cli_search.rs",
+            "wiring.rs"} <= set(files)
+    used = set()
+    for f in files:
+        used |= set(re.findall(r"\bsys::((?:oi|OI)_[A-Za-z0-9_]+)", open(os.path.join(src_dir, f)).read()))
+    assert "oi_search_hybrid" in used and "oi_index_create" in used and "oi_lexicon_analyze" in used
+    for name in sorted(used):
+        if name.startswith("oi_") and name not in ("oi_index", "oi_index_desc", "oi_bm25_params", "oi_status"):
+            assert name in declared, "rust source calls %s, which include/openintel_gpu.h does not declare" % name
+        assert re.search(r"\b%s\b" % re.escape(name), sys_rs), "rust source names sys::%s, missing from the -sys crate" % name
+    # every module lib.rs declares exists, and the use case takes the port as `&dyn HybridSearch` (drop-in injection)
+    lib_rs = open(os.path.join(src_dir, "lib.rs")).read()
+    for mod in re.findall(r"pub mod ([a-z_]+);", lib_rs):
+        assert mod + ".rs" in files, mod
+    app = open(os.path.join(src_dir, "application_search.rs")).read()
+    assert "searcher: &dyn HybridSearch" in app and "pub async fn search(" in app
+    assert "pub struct SearchPostsArgs" in open(os.path.join(src_dir, "mcp_search.rs")).read()
+    assert "pub struct SearchArgs" in open(os.path.join(src_dir, "cli_search.rs")).read()
+
+
 def test_version_and_no_cpu_fallback(lib):
     assert "sm_100a" in oi.version()
     import torch

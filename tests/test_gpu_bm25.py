@@ -361,3 +361,4 @@ def test_gpu_matches_the_published_formulas_on_hand_sized_input(oi):
         assert [int(i) for i in h_ids[0][:len(order)]] == order
         for d, v in zip(h_ids[0][:len(order)], h_rrf[0]):
             assert abs(Fraction(float(v)) - fused[int(d)]) < Fraction(1, 10 ** 8)
+
