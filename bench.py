@@ -40,6 +40,8 @@ UNIT = "queries/s"
 # hybrid_overlap mode of the headline (0 = legs back to back, 1 = co-resident lite kernels, 2 = SM partition);
 # the value is the one that measured best (profiles/r02_overlap_sweep.md)
 DEFAULT_OVERLAP = 0
+# exchange of the shard-local lists at N > 1: "nccl" (ncclAllGather) or "p2p" (peer stores into IPC-mapped buffers + flags)
+DEFAULT_EXCHANGE = "p2p"
 
 
 def workload_name(n_docs):
@@ -166,7 +168,7 @@ def _dev_time(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
-def build_hybrid_index(oi, n_total, rank, world, local_rank, dist, dev, max_batch=BATCH):
+def build_hybrid_index(oi, n_total, rank, world, local_rank, dist, dev, max_batch=BATCH, p2p=True):
     """This rank's shard of an n_total-document corpus: synthetic embeddings + synthetic CSR built on the device,
     GLOBAL BM25 statistics (df, N, avgdl summed over the shards: SPEC §3 / §5), NCCL communicator for the exchange."""
     import numpy as np
@@ -197,6 +199,10 @@ def build_hybrid_index(oi, n_total, rank, world, local_rank, dist, dev, max_batc
         uid = uid.to(dev)
         dist.broadcast(uid, 0)
         ix.comm_init(rank, world, uid.cpu().numpy())
+        if p2p:  # map the peers' exchange buffers; the transport is chosen later ("comm_exchange")
+            from openintel_b200 import sharding
+            sharding.attach_p2p(dist, ix, device=dev)
+            ix.set_option("comm_exchange", 0)
     return ix, n_local, base, cdf, gdf, npost_g, avgdl
 
 
@@ -267,12 +273,17 @@ def time_hybrid(ix, dev, cdf, dist, steps, warmup, rank, local_rank, sample_cloc
     torch.cuda.synchronize()
     e2e_s = allmax(time.perf_counter() - t0)
     barrier()
-    # ---- the legs on their own (roofline: CUDA events around back-to-back calls of one leg) ----
+    # ---- the legs on their own (roofline: CUDA events around back-to-back calls of one leg).  Sharded runs time the
+    #      LOCAL part of a leg (exchange skipped): with it, every call of the loop also waits for the slowest rank ----
+    if dist is not None:
+        ix.set_option("comm_debug_skip_gather", 1)
     ids1, sc1 = d_out[0], d_rrf
     ms_cos = allmax(_dev_time(lambda i: ix.search_cosine_dev(d_q[i % n_pool], BATCH, TOPK, ids1, sc1, stream), max(5, steps // 2), 2))
     barrier()
     ms_bm = allmax(_dev_time(lambda i: ix.search_bm25_dev(d_t[i % n_pool], d_offs, BATCH, TOPK, ids1, sc1, stream), max(5, steps // 2), 2))
     barrier()
+    if dist is not None:
+        ix.set_option("comm_debug_skip_gather", 0)
     step_host(0)  # leave the result of pool entry 0 in the host buffers for the verification
     return {"ms_total": ms, "e2e_s": e2e_s, "launches": launches, "clocks": clocks, "ms_cos": ms_cos, "ms_bm25": ms_bm,
             "h2d": BATCH * DIM * 4 + BATCH * QTERMS * 4 + (BATCH + 1) * 4, "d2h": BATCH * TOPK * 16,
@@ -450,6 +461,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-size oracle comparison of the timed output")
     ap.add_argument("--repeats", type=int, default=3, help="timed regions of `steps` steps; the median is reported")
+    ap.add_argument("--exchange", default=DEFAULT_EXCHANGE, choices=["nccl", "p2p"], help="transport of the local top-k lists at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -477,6 +489,14 @@ def main():
     ix, n_local, base, cdf, gdf, npost_g, avgdl = build_hybrid_index(oi, args.docs, rank, world, local_rank, dist, dev)
     ix.set_option("hybrid_overlap", args.overlap)
     build_s = time.perf_counter() - t_build
+    other_exchange = None
+    if world > 1:
+        # the transport that is NOT the headline's is timed first, for the record (same index, same queries)
+        ix.set_option("comm_exchange", 0 if args.exchange == "p2p" else 1)
+        ro = time_hybrid(ix, dev, cdf, dist, args.steps, args.warmup, rank, local_rank, sample_clocks=False)
+        other_exchange = {"transport": "nccl" if args.exchange == "p2p" else "p2p", "ms_per_step": ro["ms_total"] / args.steps,
+                          "queries_per_s": args.steps * BATCH / (ro["ms_total"] * 1e-3)}
+        ix.set_option("comm_exchange", 1 if args.exchange == "p2p" else 0)
 
     # several timed regions; the median region is the reported one (one region per N was too noisy: VERDICT r1 weak #6)
     runs = [time_hybrid(ix, dev, cdf, dist, args.steps, args.warmup, rank, local_rank) for _ in range(max(1, args.repeats))]
@@ -525,7 +545,8 @@ def main():
                     "random unit query vectors, 8 distinct Zipf-drawn terms per query)",
             "config": {"workload": workload_name(args.docs), "n_docs": args.docs, "docs_per_gpu": n_local, "dim": DIM, "k": TOPK, "batch": BATCH,
                        "vocab": VOCAB, "query_terms": QTERMS, "rrf_k": RRF_K, "postings": int(npost_g),
-                       "parallelism": ("doc-sharded x%d, one NCCL all-gather of both modalities' local top-k + device merge, RRF on global ranks" % world) if world > 1 else "1 GPU",
+                       "parallelism": ("doc-sharded x%d, one exchange of both modalities' local top-k per batch (%s) + device merge, RRF on global ranks"
+                                       % (world, "peer-to-peer stores over NVLink into IPC-mapped buffers" if args.exchange == "p2p" else "ncclAllGather")) if world > 1 else "1 GPU",
                        "hybrid_overlap": args.overlap,
                        "l2": "a step streams %.1f GB of embeddings per GPU, far beyond the 126 MB L2; no flush needed" % (n_local * DIM * 2 / 1e9),
                        "timed_regions": "%d regions of %d steps, the median region is reported: %s ms/step" % (len(runs), args.steps, ", ".join("%.3f" % (r["ms_total"] / args.steps) for r in runs)),
@@ -545,7 +566,9 @@ def main():
                      "step_over_max_leg": step_ms / max(ms_cos, ms_bm), "step_over_sum_of_legs": step_ms / (ms_cos + ms_bm),
                      "bm25": {"postings_touched_per_query_per_gpu": df_sum, "algorithmic_posting_gbs": df_sum * 8 * BATCH / (ms_bm * 1e-3) / 1e9,
                               "bound": "issue / L2 (static ncu capture: profiles/r02_ncu_bm25.md)"},
-                     "exchange_us_per_step": exchange_us},
+                     "exchange_us_per_step": exchange_us, "exchange": args.exchange if world > 1 else None,
+                     "other_exchange": other_exchange,
+                     "p2p_status": (lambda st: {"batches": st[0], "timed_out": st[1]})(ix.p2p_status()) if (world > 1 and args.exchange == "p2p") else None},
             "cpu_baseline": cpu, "clocks": res["clocks"], "verify": verify,
         }
     ix.close()
@@ -560,6 +583,7 @@ def main():
             try:
                 ix4, n_loc4, _, cdf4, _, npost4, _ = build_hybrid_index(oi, N_DOCS_CONFIG4, rank, world, local_rank, dist, dev)
                 ix4.set_option("hybrid_overlap", args.overlap)
+                ix4.set_option("comm_exchange", 1 if args.exchange == "p2p" else 0)
                 r4 = time_hybrid(ix4, dev, cdf4, dist, max(5, args.steps // 2), 3, rank, local_rank, sample_clocks=False)
                 st4 = max(5, args.steps // 2)
                 if rank == 0:

@@ -39,6 +39,7 @@ extern "C" {
 #define OI_NO_DOC 0xFFFFFFFFu
 #define OI_MAX_K 1024u
 #define OI_UNIQUE_ID_BYTES 128
+#define OI_P2P_HANDLE_BYTES 64
 
 typedef int32_t oi_status;
 enum {
@@ -116,6 +117,16 @@ oi_status oi_comm_unique_id(uint8_t out[OI_UNIQUE_ID_BYTES]);
 oi_status oi_index_comm_init(oi_index *h, int32_t rank, int32_t world_size,
                              const uint8_t unique_id[OI_UNIQUE_ID_BYTES]);
 
+/* Optional peer-to-peer exchange (after oi_index_comm_init, all ranks on one NVLink box): instead of the all-gather,
+ * every rank pushes its local lists straight into the other ranks' exchange buffers (CUDA IPC mappings, one kernel of
+ * plain stores + an epoch flag per peer) and merges as soon as all flags have arrived.  Every rank exports the handle
+ * of its buffer, the host distributes the `world_size` handles (any transport), every rank attaches; from then on the
+ * sharded search calls use the push ("comm_exchange" option: 1 = push, 0 = back to ncclAllGather).  Results are
+ * identical.  oi_index_p2p_status reports the number of exchanges and whether any wait for a peer timed out. */
+oi_status oi_index_p2p_export(oi_index *h, uint8_t out[OI_P2P_HANDLE_BYTES]);
+oi_status oi_index_p2p_attach(oi_index *h, const uint8_t *handles /* [world_size][OI_P2P_HANDLE_BYTES] */);
+oi_status oi_index_p2p_status(oi_index *h, uint64_t *batches, uint32_t *timed_out);
+
 /* ---- search: host buffers in, host buffers out (the calls the Rust adapter binds) --------- */
 /* queries: nq x dim f32, L2-normalised.  out_ids/out_scores: nq x k. */
 oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_t nq, uint32_t k,
@@ -146,7 +157,25 @@ oi_status oi_search_hybrid_dev(oi_index *h, const float *d_queries, const uint32
 
 /* ---- batched lexicon scorer: the GPU PostAnalyzer (SPEC §8; replaces LexiconAnalyzer::analyze,
  * src/adapters/analyzer/lexicon.rs:82-87; one output per input post, aligned to input order).
- * texts = concatenated UTF-8 bytes, post i = texts[offsets[i] .. offsets[i+1]). */
+ * texts = concatenated UTF-8 bytes, post i = texts[offsets[i] .. offsets[i+1]).
+ *
+ * Handle form: the stream and the device buffers are created once (they grow on demand) and reused by every call; calls
+ * on one handle are serialised.  oi_lexicon_run can also return the reference's social summary of the batch
+ * (SpeculationEngine::social_summary, src/domain/engine/speculation_engine.rs:70-125: counts by the bull/bear threshold
+ * -- 0.2 in EngineConfig::default, src/domain/engine/config.rs:18-33 --, mean polarity summed in input order,
+ * speculation index, bull/bear ratio with -1 standing for "no bearish post"); out_summary may be NULL. */
+typedef struct oi_lexicon oi_lexicon;
+typedef struct {
+  uint64_t total, bullish, bearish, neutral;
+  double net_sentiment, speculation_index, bull_bear_ratio;
+} oi_social_summary;
+oi_status oi_lexicon_create(int32_t device, uint64_t reserve_bytes, uint64_t reserve_posts, oi_lexicon **out);
+void oi_lexicon_destroy(oi_lexicon *lx);
+oi_status oi_lexicon_run(oi_lexicon *lx, const uint8_t *texts, const uint64_t *offsets, uint64_t n_posts,
+                         double *out_polarity, uint8_t *out_speculative, uint32_t *out_bull_hits,
+                         uint32_t *out_bear_hits, double bull_bear_threshold, oi_social_summary *out_summary);
+uint64_t oi_lexicon_launch_count(const oi_lexicon *lx);
+/* convenience form on a per-device handle the library keeps for the life of the process */
 oi_status oi_lexicon_analyze(int32_t device, const uint8_t *texts, const uint64_t *offsets,
                              uint64_t n_posts, double *out_polarity, uint8_t *out_speculative,
                              uint32_t *out_bull_hits, uint32_t *out_bear_hits);

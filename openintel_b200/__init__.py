@@ -6,7 +6,7 @@ openintel_b200/host/ mirrors the reference's port/adapter conventions.  There is
 fallback: importing works anywhere, but every compute call needs the CUDA library and a GPU.
 """
 from .capi import (GpuIndex, OiError, NO_DOC, DTYPE_F32, DTYPE_BF16, lib_path, load_library,  # noqa: F401
-                   lexicon_analyze, version)
+                   lexicon_analyze, version, GpuLexicon, pack_texts)
 
 __all__ = ["GpuIndex", "OiError", "NO_DOC", "DTYPE_F32", "DTYPE_BF16", "lib_path", "load_library",
-           "lexicon_analyze", "version"]
+           "lexicon_analyze", "version", "GpuLexicon", "pack_texts"]

@@ -9,6 +9,7 @@ import numpy as np
 NO_DOC = 0xFFFFFFFF
 DTYPE_F32, DTYPE_BF16 = 0, 1
 UNIQUE_ID_BYTES = 128
+P2P_HANDLE_BYTES = 64
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 STATUS_NAMES = {1: "INVALID_ARG", 2: "NO_DEVICE", 3: "CUDA", 4: "OUT_OF_MEMORY", 5: "STATE", 6: "COMM", 7: "UNSUPPORTED"}
@@ -30,6 +31,12 @@ class IndexDesc(C.Structure):
 class Bm25Params(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("k1", C.c_float), ("b", C.c_float), ("avgdl", C.c_float),
                 ("n_docs_global", C.c_uint64), ("global_df", C.POINTER(C.c_uint32))]
+
+
+class SocialSummary(C.Structure):
+    """oi_social_summary: SpeculationEngine::social_summary of a batch (src/domain/engine/speculation_engine.rs:70-125)"""
+    _fields_ = [("total", C.c_uint64), ("bullish", C.c_uint64), ("bearish", C.c_uint64), ("neutral", C.c_uint64),
+                ("net_sentiment", C.c_double), ("speculation_index", C.c_double), ("bull_bear_ratio", C.c_double)]
 
 
 def lib_path():
@@ -67,6 +74,9 @@ def load_library():
         "oi_index_read_bm25": (st, [H, _u64p, _u32p, _u32p, _u32p, _f32p]),
         "oi_comm_unique_id": (st, [_vp]),
         "oi_index_comm_init": (st, [H, C.c_int32, C.c_int32, _vp]),
+        "oi_index_p2p_export": (st, [H, _vp]),
+        "oi_index_p2p_attach": (st, [H, _vp]),
+        "oi_index_p2p_status": (st, [H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
         "oi_search_cosine": (st, [H, _f32p, C.c_uint32, C.c_uint32, _u32p, _f32p]),
         "oi_search_bm25": (st, [H, _u32p, _u32p, C.c_uint32, C.c_uint32, _u32p, _f32p]),
         "oi_search_hybrid": (st, [H, _f32p, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, _f32p, _u32p, _u32p]),
@@ -74,6 +84,10 @@ def load_library():
         "oi_search_bm25_dev": (st, [H, _u32p, _u32p, C.c_uint32, C.c_uint32, _u32p, _f32p, _vp]),
         "oi_search_hybrid_dev": (st, [H, _f32p, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, _f32p, _u32p, _u32p, _vp]),
         "oi_lexicon_analyze": (st, [C.c_int32, _vp, _u64p, C.c_uint64, _vp, _vp, _u32p, _u32p]),
+        "oi_lexicon_create": (st, [C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(H)]),
+        "oi_lexicon_destroy": (None, [H]),
+        "oi_lexicon_run": (st, [H, _vp, _u64p, C.c_uint64, _vp, _vp, _u32p, _u32p, C.c_double, C.POINTER(SocialSummary)]),
+        "oi_lexicon_launch_count": (C.c_uint64, [H]),
         "oi_index_launch_count": (C.c_uint64, [H]),
         "oi_index_set_option": (st, [H, C.c_char_p, C.c_int64]),
         "oi_debug_cosine_gemm_scores": (st, [H, _f32p, C.c_uint32, _f32p]),
@@ -201,6 +215,21 @@ class GpuIndex:
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         self._ck(self.L.oi_index_comm_init(self.h, rank, world, _addr(uid)))
 
+    def p2p_export(self):
+        """handle (64 bytes) of this rank's exchange buffer: distribute to every rank, then p2p_attach"""
+        buf = np.zeros(P2P_HANDLE_BYTES, dtype=np.uint8)
+        self._ck(self.L.oi_index_p2p_export(self.h, _addr(buf)))
+        return buf
+
+    def p2p_attach(self, handles):
+        hs = np.ascontiguousarray(handles, dtype=np.uint8).reshape(-1, P2P_HANDLE_BYTES)
+        self._ck(self.L.oi_index_p2p_attach(self.h, _addr(hs)))
+
+    def p2p_status(self):
+        n, bad = C.c_uint64(), C.c_uint32()
+        self._ck(self.L.oi_index_p2p_status(self.h, C.byref(n), C.byref(bad)))
+        return n.value, bool(bad.value)
+
     # -- search, host buffers (numpy or pinned torch tensors)
     @staticmethod
     def _pack_terms(q_terms):
@@ -269,6 +298,63 @@ class GpuIndex:
 
     def set_option(self, name, value):
         self._ck(self.L.oi_index_set_option(self.h, name.encode(), int(value)))
+
+
+def pack_texts(texts):
+    """list of str -> (UTF-8 blob u8[], offsets u64[n + 1]) as the lexicon entry points take them"""
+    raw = [t.encode("utf-8") for t in texts]
+    offs = np.zeros(len(raw) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in raw])
+    blob = np.frombuffer(b"".join(raw) or b"\0", dtype=np.uint8).copy()
+    return blob, offs
+
+
+class GpuLexicon:
+    """The handle form of the GPU PostAnalyzer (oi_lexicon_*): stream and device buffers live as long as the object."""
+
+    def __init__(self, device=0, reserve_bytes=1 << 20, reserve_posts=1 << 12):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        s = self.L.oi_lexicon_create(device, reserve_bytes, reserve_posts, C.byref(self.h))
+        if s:
+            self.h = None
+            raise OiError(s, self.L.oi_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.oi_lexicon_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def run_packed(self, blob, offs, summary=False, threshold=0.2):
+        """(blob, offsets) from pack_texts -> (polarity f64[n], speculative bool[n], bull u32[n], bear u32[n][, summary dict])"""
+        n = len(offs) - 1
+        pol = np.empty(n, dtype=np.float64)
+        spec = np.empty(n, dtype=np.uint8)
+        bull = np.empty(n, dtype=np.uint32)
+        bear = np.empty(n, dtype=np.uint32)
+        sm = SocialSummary()
+        s = self.L.oi_lexicon_run(self.h, _addr(blob), _addr(offs), n, _addr(pol), _addr(spec), _addr(bull), _addr(bear),
+                                  threshold, C.byref(sm) if summary else None)
+        if s:
+            raise OiError(s, self.L.oi_last_error(None).decode())
+        out = (pol, spec.astype(bool), bull, bear)
+        if summary:
+            out += ({f: getattr(sm, f) for f, _ in SocialSummary._fields_},)
+        return out
+
+    def analyze(self, texts, summary=False, threshold=0.2):
+        return self.run_packed(*pack_texts(texts), summary=summary, threshold=threshold)
+
+    def launch_count(self):
+        return int(self.L.oi_lexicon_launch_count(self.h))
 
 
 def lexicon_analyze(texts, device=0):

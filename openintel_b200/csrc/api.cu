@@ -257,6 +257,11 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     h->no_pinned_staging = (int)value;
     return OI_OK;
   }
+  if (!strcmp(name, "comm_exchange")) {  // 0 = ncclAllGather, 1 = peer-to-peer push (needs oi_index_p2p_attach)
+    OI_REQUIRE(value == 0 || value == 1, "comm_exchange must be 0 (NCCL all-gather) or 1 (peer-to-peer push)");
+    h->comm_exchange = (int)value;
+    return OI_OK;
+  }
   if (!strcmp(name, "comm_debug_skip_gather")) {
     h->comm_skip = (int)value;
     return OI_OK;

@@ -79,6 +79,7 @@ struct oi_index {
   OiComm *comm = nullptr;
   int rank = 0, world = 1;
   int comm_skip = 0;  // timing experiments only: skip the all-gather (results are then shard-local garbage)
+  int comm_exchange = 0;  // 0 = ncclAllGather, 1 = peer-to-peer push over mapped buffers (set by oi_index_p2p_attach)
 
   uint32_t esize() const { return desc.dtype == OI_DTYPE_F32 ? 4u : 2u; }
   oi_status fail(oi_status code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));

@@ -10,7 +10,17 @@
 // a token gathers its (<= 9 relevant) normalised bytes into a 128-bit word and compares it with
 // the packed BULL / BEAR / JARGON tables.  Integer hit counts are exact; polarity is one f64
 // divide (Polarity::new clamps to [-1, 1], src/domain/values/polarity.rs:8-14).
-// HBM-bound byte scan: algorithmic bytes = the text bytes, read once.
+// The post is staged once into shared memory (coalesced 16-byte loads; posts longer than the staging area are read in
+// place), so the tokenizer's look-back / look-ahead reads never go back to global memory: algorithmic bytes = the text
+// bytes, read once.  The kernel is instruction-bound, not HBM-bound (~25 instructions per byte); see
+// profiles/r02_ncu_lexicon.md.
+//
+// Handle-based API (round 2): oi_lexicon_create allocates the stream and the device buffers once; oi_lexicon_run reuses
+// them (they grow on demand) and can fuse the reference's social summary (SpeculationEngine::social_summary,
+// src/domain/engine/speculation_engine.rs:70-125) into the same call.  oi_lexicon_analyze keeps its round-1 signature
+// on top of a per-device cached handle.
+#include <map>
+#include <mutex>
 #include <string>
 
 #include "internal.h"
@@ -59,15 +69,31 @@ __device__ __forceinline__ int classify(const uint8_t *t, long long i, long long
   return CLS_SEP;
 }
 
+constexpr int kStageBytes = 4096;  // per warp: posts up to this many bytes are tokenized from shared memory
+
 __global__ void __launch_bounds__(256) lexicon_kernel(const uint8_t *texts, const unsigned long long *offsets,
                                                       unsigned long long n_posts, double *polarity,
                                                       uint8_t *speculative, uint32_t *bull_hits, uint32_t *bear_hits) {
+  __shared__ __align__(16) uint8_t s_stage[8][kStageBytes + 32];
   const int lane = threadIdx.x & 31;
   const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  uint8_t *stage = s_stage[threadIdx.x >> 5];
   for (unsigned long long post = warp; post < n_posts; post += n_warps) {
     const uint8_t *t = texts + offsets[post];
     const long long len = (long long)(offsets[post + 1] - offsets[post]);
+    if (len <= kStageBytes) {
+      // the 16-byte words that cover the post, loaded aligned (the allocation is padded to whole words); the post's
+      // first byte sits at `sh` inside the staged copy
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(t) & ~(uintptr_t)15;
+      const int sh = (int)(reinterpret_cast<uintptr_t>(t) - a0);
+      const int n_words = (int)((sh + len + 15) >> 4);
+      __syncwarp();  // the previous post's readers are done with the staging area
+      for (int w = lane; w < n_words; w += 32)
+        reinterpret_cast<uint4 *>(stage)[w] = __ldg(reinterpret_cast<const uint4 *>(a0) + w);
+      __syncwarp();
+      t = stage + sh;
+    }
     uint32_t bull = 0, bear = 0, spec = 0;
     for (long long i = lane; i < len; i += 32) {
       const int c = classify(t, i, len);
@@ -126,59 +152,171 @@ __global__ void __launch_bounds__(256) lexicon_kernel(const uint8_t *texts, cons
 
 void oi_set_thread_error(const std::string &msg);  // api.cu
 
-extern "C" oi_status oi_lexicon_analyze(int32_t device, const uint8_t *texts, const uint64_t *offsets,
-                                        uint64_t n_posts, double *out_polarity, uint8_t *out_speculative,
-                                        uint32_t *out_bull_hits, uint32_t *out_bear_hits) {
-  auto fail = [](oi_status code, const std::string &m) { oi_set_thread_error(m); return code; };
-  if (n_posts == 0) return OI_OK;
-  if (!offsets || !out_polarity || !out_speculative) return fail(OI_ERR_INVALID_ARG, "NULL offsets / output pointer");
-  for (uint64_t i = 0; i < n_posts; ++i)
-    if (offsets[i + 1] < offsets[i]) return fail(OI_ERR_INVALID_ARG, "offsets not monotone");
-  const uint64_t n_bytes = offsets[n_posts] - offsets[0];
-  if (n_bytes && !texts) return fail(OI_ERR_INVALID_ARG, "texts is NULL");
-  int n_dev = 0;
-  cudaError_t e = cudaGetDeviceCount(&n_dev);
-  if (e != cudaSuccess || n_dev == 0) return fail(OI_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
-  if (device < 0 || device >= n_dev) return fail(OI_ERR_INVALID_ARG, "device ordinal out of range");
+// One thread: the reference's social summary over the batch's signals, in the reference's order (a sequential f64 sum:
+// src/domain/engine/speculation_engine.rs:76-84), so that the mean is bit-identical to SpeculationEngine's.
+__global__ void social_summary_kernel(const double *polarity, const uint8_t *speculative, unsigned long long n, double thr,
+                                      oi_social_summary *out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned long long bullish = 0, bearish = 0, neutral = 0, spec = 0;
+  double sum = 0.0;
+  for (unsigned long long i = 0; i < n; ++i) {
+    const double v = polarity[i];
+    sum += v;
+    if (v > thr) ++bullish;
+    else if (v < -thr) ++bearish;
+    else ++neutral;
+    spec += speculative[i] != 0;
+  }
+  double net = n == 0 ? 0.0 : sum / (double)n;
+  double si = n == 0 ? 0.0 : (double)spec / (double)n;
+  net = net > 1.0 ? 1.0 : (net < -1.0 ? -1.0 : net);
+  si = si > 1.0 ? 1.0 : (si < 0.0 ? 0.0 : si);
+  out->total = n; out->bullish = bullish; out->bearish = bearish; out->neutral = neutral;
+  out->net_sentiment = net; out->speculation_index = si;
+  out->bull_bear_ratio = bearish == 0 ? -1.0 : (double)bullish / (double)bearish;
+}
+
+struct oi_lexicon {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::mutex mu;
   uint8_t *d_text = nullptr, *d_spec = nullptr;
   unsigned long long *d_off = nullptr;
   double *d_pol = nullptr;
   uint32_t *d_bull = nullptr, *d_bear = nullptr;
-  cudaStream_t st = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_text); cudaFree(d_spec); cudaFree(d_off); cudaFree(d_pol); cudaFree(d_bull); cudaFree(d_bear);
-    if (st) cudaStreamDestroy(st);
-  };
+  oi_social_summary *d_sum = nullptr;
+  size_t cap_bytes = 0, cap_posts = 0;
+  uint64_t launches = 0;
+};
+
+static oi_status lx_fail(oi_status code, const std::string &m) { oi_set_thread_error(m); return code; }
+
 #define LX_CK(call)                                                                                  \
   do {                                                                                               \
     cudaError_t e_ = (call);                                                                         \
-    if (e_ != cudaSuccess) {                                                                         \
-      cleanup();                                                                                     \
-      return fail(e_ == cudaErrorMemoryAllocation ? OI_ERR_OUT_OF_MEMORY : OI_ERR_CUDA,              \
-                  std::string(#call " failed: ") + cudaGetErrorString(e_));                          \
-    }                                                                                                \
+    if (e_ != cudaSuccess)                                                                           \
+      return lx_fail(e_ == cudaErrorMemoryAllocation ? OI_ERR_OUT_OF_MEMORY : OI_ERR_CUDA,           \
+                     std::string(#call " failed: ") + cudaGetErrorString(e_));                       \
   } while (0)
-  LX_CK(cudaSetDevice(device));
-  LX_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  LX_CK(cudaMalloc(&d_text, n_bytes ? n_bytes : 1));
-  LX_CK(cudaMalloc(&d_off, (n_posts + 1) * sizeof(unsigned long long)));
-  LX_CK(cudaMalloc(&d_pol, n_posts * sizeof(double)));
-  LX_CK(cudaMalloc(&d_spec, n_posts));
-  LX_CK(cudaMalloc(&d_bull, n_posts * sizeof(uint32_t)));
-  LX_CK(cudaMalloc(&d_bear, n_posts * sizeof(uint32_t)));
-  if (n_bytes) LX_CK(cudaMemcpyAsync(d_text, texts + offsets[0], n_bytes, cudaMemcpyHostToDevice, st));
-  // offsets are rebased to the copied blob on the device side by passing texts - offsets[0]
-  LX_CK(cudaMemcpyAsync(d_off, offsets, (n_posts + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-  uint64_t blocks = (n_posts + 7) / 8;
-  if (blocks > 148ull * 16) blocks = 148ull * 16;
-  lexicon_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_text - offsets[0], d_off, n_posts, d_pol, d_spec, d_bull, d_bear);
-  LX_CK(cudaGetLastError());
-  LX_CK(cudaMemcpyAsync(out_polarity, d_pol, n_posts * sizeof(double), cudaMemcpyDeviceToHost, st));
-  LX_CK(cudaMemcpyAsync(out_speculative, d_spec, n_posts, cudaMemcpyDeviceToHost, st));
-  if (out_bull_hits) LX_CK(cudaMemcpyAsync(out_bull_hits, d_bull, n_posts * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  if (out_bear_hits) LX_CK(cudaMemcpyAsync(out_bear_hits, d_bear, n_posts * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  LX_CK(cudaStreamSynchronize(st));
-#undef LX_CK
-  cleanup();
+
+// (re)allocates the device buffers so that a batch of `bytes` text bytes / `posts` posts fits
+static oi_status lx_reserve(oi_lexicon *lx, size_t bytes, size_t posts) {
+  if (bytes > lx->cap_bytes) {
+    cudaFree(lx->d_text);
+    lx->d_text = nullptr;
+    lx->cap_bytes = 0;
+    const size_t want = bytes + bytes / 4 + 64;  // + two 16-byte words: the staging loads read whole aligned words
+    LX_CK(cudaMalloc(&lx->d_text, want + 32));
+    lx->cap_bytes = want;
+  }
+  if (posts > lx->cap_posts) {
+    cudaFree(lx->d_off); cudaFree(lx->d_pol); cudaFree(lx->d_spec); cudaFree(lx->d_bull); cudaFree(lx->d_bear);
+    lx->d_off = nullptr; lx->d_pol = nullptr; lx->d_spec = nullptr; lx->d_bull = nullptr; lx->d_bear = nullptr;
+    lx->cap_posts = 0;
+    const size_t want = posts + posts / 4 + 16;
+    LX_CK(cudaMalloc(&lx->d_off, (want + 1) * sizeof(unsigned long long)));
+    LX_CK(cudaMalloc(&lx->d_pol, want * sizeof(double)));
+    LX_CK(cudaMalloc(&lx->d_spec, want));
+    LX_CK(cudaMalloc(&lx->d_bull, want * sizeof(uint32_t)));
+    LX_CK(cudaMalloc(&lx->d_bear, want * sizeof(uint32_t)));
+    lx->cap_posts = want;
+  }
   return OI_OK;
 }
+
+extern "C" oi_status oi_lexicon_create(int32_t device, uint64_t reserve_bytes, uint64_t reserve_posts, oi_lexicon **out) {
+  if (!out) return lx_fail(OI_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return lx_fail(OI_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+  if (device < 0 || device >= n_dev) return lx_fail(OI_ERR_INVALID_ARG, "device ordinal out of range");
+  oi_lexicon *lx = new (std::nothrow) oi_lexicon();
+  if (!lx) return lx_fail(OI_ERR_OUT_OF_MEMORY, "host allocation failed");
+  lx->device = device;
+  oi_status s = OI_OK;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&lx->st, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc(&lx->d_sum, sizeof(oi_social_summary))) != cudaSuccess)
+    s = lx_fail(OI_ERR_CUDA, std::string("lexicon handle: ") + cudaGetErrorString(e));
+  if (s == OI_OK) s = lx_reserve(lx, (size_t)reserve_bytes, (size_t)reserve_posts);
+  if (s != OI_OK) { oi_lexicon_destroy(lx); return s; }
+  *out = lx;
+  return OI_OK;
+}
+
+extern "C" void oi_lexicon_destroy(oi_lexicon *lx) {
+  if (!lx) return;
+  cudaSetDevice(lx->device);
+  if (lx->st) cudaStreamSynchronize(lx->st);
+  cudaFree(lx->d_text); cudaFree(lx->d_off); cudaFree(lx->d_pol); cudaFree(lx->d_spec); cudaFree(lx->d_bull); cudaFree(lx->d_bear);
+  cudaFree(lx->d_sum);
+  if (lx->st) cudaStreamDestroy(lx->st);
+  delete lx;
+}
+
+extern "C" oi_status oi_lexicon_run(oi_lexicon *lx, const uint8_t *texts, const uint64_t *offsets, uint64_t n_posts,
+                                    double *out_polarity, uint8_t *out_speculative, uint32_t *out_bull_hits,
+                                    uint32_t *out_bear_hits, double bull_bear_threshold, oi_social_summary *out_summary) {
+  if (!lx) return lx_fail(OI_ERR_INVALID_ARG, "lexicon handle is NULL");
+  std::lock_guard<std::mutex> lock(lx->mu);
+  if (n_posts == 0) {
+    if (out_summary) { *out_summary = oi_social_summary(); out_summary->bull_bear_ratio = -1.0; }
+    return OI_OK;
+  }
+  if (!offsets || !out_polarity || !out_speculative) return lx_fail(OI_ERR_INVALID_ARG, "NULL offsets / output pointer");
+  for (uint64_t i = 0; i < n_posts; ++i)
+    if (offsets[i + 1] < offsets[i]) return lx_fail(OI_ERR_INVALID_ARG, "offsets not monotone");
+  const uint64_t n_bytes = offsets[n_posts] - offsets[0];
+  if (n_bytes && !texts) return lx_fail(OI_ERR_INVALID_ARG, "texts is NULL");
+  LX_CK(cudaSetDevice(lx->device));
+  oi_status s = lx_reserve(lx, (size_t)n_bytes, (size_t)n_posts);
+  if (s) return s;
+  cudaStream_t st = lx->st;
+  // the blob lands 16-byte aligned at d_text + 16, so that the word-wise staging of the first post may read the word below
+  uint8_t *d_blob = lx->d_text + 16;
+  if (n_bytes) LX_CK(cudaMemcpyAsync(d_blob, texts + offsets[0], n_bytes, cudaMemcpyHostToDevice, st));
+  LX_CK(cudaMemcpyAsync(lx->d_off, offsets, (n_posts + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  uint64_t blocks = (n_posts + 7) / 8;
+  if (blocks > 148ull * 8) blocks = 148ull * 8;
+  // offsets are rebased to the copied blob on the device side by passing the blob pointer minus offsets[0]
+  lexicon_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_blob - offsets[0], lx->d_off, n_posts, lx->d_pol, lx->d_spec, lx->d_bull, lx->d_bear);
+  ++lx->launches;
+  LX_CK(cudaGetLastError());
+  if (out_summary) {
+    social_summary_kernel<<<1, 32, 0, st>>>(lx->d_pol, lx->d_spec, n_posts, bull_bear_threshold, lx->d_sum);
+    ++lx->launches;
+    LX_CK(cudaGetLastError());
+    LX_CK(cudaMemcpyAsync(out_summary, lx->d_sum, sizeof(oi_social_summary), cudaMemcpyDeviceToHost, st));
+  }
+  LX_CK(cudaMemcpyAsync(out_polarity, lx->d_pol, n_posts * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LX_CK(cudaMemcpyAsync(out_speculative, lx->d_spec, n_posts, cudaMemcpyDeviceToHost, st));
+  if (out_bull_hits) LX_CK(cudaMemcpyAsync(out_bull_hits, lx->d_bull, n_posts * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (out_bear_hits) LX_CK(cudaMemcpyAsync(out_bear_hits, lx->d_bear, n_posts * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  LX_CK(cudaStreamSynchronize(st));
+  return OI_OK;
+}
+
+extern "C" uint64_t oi_lexicon_launch_count(const oi_lexicon *lx) { return lx ? lx->launches : 0; }
+
+// round-1 entry point: the same call on a per-device handle that is created on first use and kept for the process
+extern "C" oi_status oi_lexicon_analyze(int32_t device, const uint8_t *texts, const uint64_t *offsets,
+                                        uint64_t n_posts, double *out_polarity, uint8_t *out_speculative,
+                                        uint32_t *out_bull_hits, uint32_t *out_bear_hits) {
+  static std::mutex mu;
+  static std::map<int, oi_lexicon *> cache;
+  oi_lexicon *lx = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(device);
+    if (it == cache.end()) {
+      oi_status s = oi_lexicon_create(device, 1 << 20, 1 << 12, &lx);
+      if (s) return s;
+      cache[device] = lx;
+    } else {
+      lx = it->second;
+    }
+  }
+  return oi_lexicon_run(lx, texts, offsets, n_posts, out_polarity, out_speculative, out_bull_hits, out_bear_hits, 0.2, nullptr);
+}
+#undef LX_CK

@@ -4,6 +4,10 @@
 // then one line per post "signal i polarity speculative" from the GPU PostAnalyzer.
 //   host_demo --store <posts.db> <queries.txt> <query_embeddings.f32> <k>
 // lifts the index out of a SQLite post store (openintel_store.hpp) and prints "hit q rank doc_id rrf rc rb post_id".
+//   host_demo --lexicon-bench <n_posts> [reps]
+// GPU PostAnalyzer throughput without any Python in the loop: n_posts synthetic posts are packed once in C++, then
+// `reps` calls of the handle API are timed (host buffers in, host buffers out); prints posts/s and text GB/s.
+#include <chrono>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -60,7 +64,48 @@ static int store_mode(int argc, char **argv) {
   return 0;
 }
 
+static int lexicon_bench(int argc, char **argv) {
+  if (argc < 3) { std::fprintf(stderr, "usage: host_demo --lexicon-bench n_posts [reps]\n"); return 2; }
+  const size_t n = std::stoul(argv[2]);
+  const int reps = argc > 3 ? std::stoi(argv[3]) : 10;
+  static const char *kWords[] = {"AAPL", "to", "the", "moon", "calls", "puts", "0dte", "yolo", "dump", "rally", "bagholder", "earnings", "holding",
+                                 "$TSLA,", "squeeze", "red", "green", "today", "market", "is", "up", "down", "a", "lot"};
+  std::string blob;
+  std::vector<uint64_t> offs{0};
+  uint64_t x = 88172645463325252ull;
+  for (size_t i = 0; i < n; ++i) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    const int len = 8 + (int)(x % 40);  // ~28 words, ~150 bytes: a typical post
+    for (int w = 0; w < len; ++w) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+      blob += kWords[x % (sizeof(kWords) / sizeof(kWords[0]))];
+      blob += ' ';
+    }
+    offs.push_back(blob.size());
+  }
+  std::vector<double> pol(n);
+  std::vector<uint8_t> spec(n);
+  GpuLexiconAnalyzer an(0);
+  oi_social_summary sum{};
+  an.run_packed(reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), n, pol.data(), spec.data(), &sum);  // warm-up, buffers grow
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; ++r) an.run_packed(reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), n, pol.data(), spec.data(), nullptr);
+  const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+  std::printf("lexicon-bench posts %zu bytes %zu ms_per_call %.3f posts_per_s %.0f text_GBps %.3f bullish %llu bearish %llu neutral %llu net %.6f\n", n,
+              blob.size(), s * 1e3, n / s, blob.size() / s / 1e9, (unsigned long long)sum.bullish, (unsigned long long)sum.bearish,
+              (unsigned long long)sum.neutral, sum.net_sentiment);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 2 && std::string(argv[1]) == "--lexicon-bench") {
+    try {
+      return lexicon_bench(argc, argv);
+    } catch (const std::exception &e) {
+      std::fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
   if (argc >= 2 && std::string(argv[1]) == "--store") {
     try {
       return store_mode(argc, argv);

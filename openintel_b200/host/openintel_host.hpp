@@ -260,11 +260,43 @@ class GpuHybridSearch final : public HybridSearch {
   uint32_t dim_, rrf_k_;
 };
 
-// Replaces LexiconAnalyzer::analyze (src/adapters/analyzer/lexicon.rs:82-87) with the batched GPU scorer.
+// The reference's social summary (SpeculationEngine::social_summary, src/domain/engine/speculation_engine.rs:70-125).
+struct SocialSummary {
+  uint64_t total = 0, bullish = 0, bearish = 0, neutral = 0;
+  double net_sentiment = 0.0, speculation_index = 0.0;
+  double bull_bear_ratio = -1.0;  // -1: no bearish post (the reference's Option::None)
+};
+
+// Replaces LexiconAnalyzer::analyze (src/adapters/analyzer/lexicon.rs:82-87) with the batched GPU scorer.  Owns an
+// oi_lexicon handle: the stream and the device buffers are created once and reused by every call.
 class GpuLexiconAnalyzer final : public PostAnalyzer {
  public:
-  explicit GpuLexiconAnalyzer(int device = 0) : device_(device) {}
-  std::vector<PostSignal> analyze(const std::vector<SocialPost> &posts) const override {
+  explicit GpuLexiconAnalyzer(int device = 0) {
+    if (oi_lexicon_create(device, 1u << 20, 1u << 12, &lx_) != OI_OK) throw DomainError::source_failure("gpu-lexicon", oi_last_error(nullptr));
+  }
+  ~GpuLexiconAnalyzer() override { oi_lexicon_destroy(lx_); }
+  GpuLexiconAnalyzer(const GpuLexiconAnalyzer &) = delete;
+  GpuLexiconAnalyzer &operator=(const GpuLexiconAnalyzer &) = delete;
+
+  std::vector<PostSignal> analyze(const std::vector<SocialPost> &posts) const override { return run(posts, nullptr); }
+  // analyze + the batch's social summary in the same call (bull/bear threshold of EngineConfig::default: 0.2)
+  std::vector<PostSignal> analyze(const std::vector<SocialPost> &posts, SocialSummary *summary, double threshold = 0.2) const {
+    oi_social_summary s{};
+    std::vector<PostSignal> out = run(posts, summary ? &s : nullptr, threshold);
+    if (summary) {
+      summary->total = s.total; summary->bullish = s.bullish; summary->bearish = s.bearish; summary->neutral = s.neutral;
+      summary->net_sentiment = s.net_sentiment; summary->speculation_index = s.speculation_index; summary->bull_bear_ratio = s.bull_bear_ratio;
+    }
+    return out;
+  }
+  // packed form (texts already concatenated): what a caller with its own buffers uses; returns seconds spent in the call
+  void run_packed(const uint8_t *blob, const uint64_t *offs, uint64_t n, double *pol, uint8_t *spec, oi_social_summary *summary = nullptr) const {
+    if (oi_lexicon_run(lx_, blob, offs, n, pol, spec, nullptr, nullptr, 0.2, summary) != OI_OK)
+      throw DomainError::source_failure("gpu-lexicon", oi_last_error(nullptr));
+  }
+
+ private:
+  std::vector<PostSignal> run(const std::vector<SocialPost> &posts, oi_social_summary *summary, double threshold = 0.2) const {
     std::string blob;
     std::vector<uint64_t> offs{0};
     for (const SocialPost &p : posts) {
@@ -274,18 +306,16 @@ class GpuLexiconAnalyzer final : public PostAnalyzer {
     const size_t n = posts.size();
     std::vector<double> pol(n);
     std::vector<uint8_t> spec(n);
-    if (n == 0) return {};
     if (blob.empty()) blob.push_back('\0');
-    if (oi_lexicon_analyze(device_, reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), n, pol.data(), spec.data(), nullptr, nullptr) != OI_OK)
+    if (oi_lexicon_run(lx_, reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), n, pol.data(), spec.data(), nullptr, nullptr, threshold,
+                       summary) != OI_OK)
       throw DomainError::source_failure("gpu-lexicon", oi_last_error(nullptr));
     std::vector<PostSignal> out(n);
     for (size_t i = 0; i < n; ++i) out[i] = PostSignal{pol[i], spec[i] != 0};
     if (out.size() != posts.size()) throw DomainError(DomainError::AnalyzerMismatch, "", "analyzer returned a different number of signals");
     return out;
   }
-
- private:
-  int device_;
+  oi_lexicon *lx_ = nullptr;
 };
 
 }  // namespace openintel

@@ -52,6 +52,17 @@ def broadcast_unique_id(dist, device="cpu"):
     return uid.cpu().numpy()
 
 
+def attach_p2p(dist, ix, device="cpu"):
+    """Switch a shard's exchange from ncclAllGather to the peer-to-peer push (all ranks on one NVLink box): every rank
+    exports the IPC handle of its exchange buffer, the handles are all-gathered through torch.distributed (control
+    plane), every rank maps its peers' buffers."""
+    import torch
+    mine = torch.from_numpy(ix.p2p_export().copy()).to(device)
+    allh = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(allh, mine)
+    ix.p2p_attach(np.stack([t.cpu().numpy() for t in allh]))
+
+
 def merge_lists_host(ids_per_rank, scores_per_rank, k):
     """Reference model of the device merge for tests: G lists [nq][k] -> best k by SPEC §1 order
     (score desc, doc id asc; NO_DOC padding dropped).  Not used by the product path."""
@@ -73,7 +84,7 @@ class ShardedIndex:
     """One rank's shard of a doc-sharded hybrid index.  Builds the shard (synthetic, SPEC §9, or
     from caller-provided arrays), agrees on global BM25 statistics and wires the communicator."""
 
-    def __init__(self, n_docs_global, dim, dtype=capi.DTYPE_F32, dist=None, device_index=0, max_k=100, max_batch=1):
+    def __init__(self, n_docs_global, dim, dtype=capi.DTYPE_F32, dist=None, device_index=0, max_k=100, max_batch=1, exchange="nccl"):
         self.dist = dist if (dist is not None and dist.get_world_size() > 1) else None
         self.rank = self.dist.get_rank() if self.dist else 0
         self.world = self.dist.get_world_size() if self.dist else 1
@@ -85,6 +96,8 @@ class ShardedIndex:
         if self.dist:
             uid = broadcast_unique_id(self.dist, device="cuda:%d" % device_index)
             self.ix.comm_init(self.rank, self.world, uid)
+            if exchange == "p2p":
+                attach_p2p(self.dist, self.ix, device="cuda:%d" % device_index)
 
     def synth(self, seed, vocab=None, zipf_cdf=None, k1=1.2, b=0.75):
         self.ix.synth_embeddings(seed)

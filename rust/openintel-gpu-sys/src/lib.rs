@@ -15,12 +15,31 @@ pub const OI_ERR_UNSUPPORTED: oi_status = 7;
 pub const OI_NO_DOC: u32 = 0xFFFF_FFFF;
 pub const OI_MAX_K: u32 = 1024;
 pub const OI_UNIQUE_ID_BYTES: usize = 128;
+pub const OI_P2P_HANDLE_BYTES: usize = 64;
 pub const OI_DTYPE_F32: u32 = 0;
 pub const OI_DTYPE_BF16: u32 = 1;
 
 #[repr(C)]
 pub struct oi_index {
     _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct oi_lexicon {
+    _private: [u8; 0],
+}
+
+/// SpeculationEngine::social_summary of a batch (src/domain/engine/speculation_engine.rs:70-125)
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct oi_social_summary {
+    pub total: u64,
+    pub bullish: u64,
+    pub bearish: u64,
+    pub neutral: u64,
+    pub net_sentiment: f64,
+    pub speculation_index: f64,
+    pub bull_bear_ratio: f64,
 }
 
 #[repr(C)]
@@ -65,6 +84,9 @@ extern "C" {
 
     pub fn oi_comm_unique_id(out: *mut u8) -> oi_status;
     pub fn oi_index_comm_init(h: *mut oi_index, rank: i32, world_size: i32, unique_id: *const u8) -> oi_status;
+    pub fn oi_index_p2p_export(h: *mut oi_index, out: *mut u8) -> oi_status;
+    pub fn oi_index_p2p_attach(h: *mut oi_index, handles: *const u8) -> oi_status;
+    pub fn oi_index_p2p_status(h: *mut oi_index, batches: *mut u64, timed_out: *mut u32) -> oi_status;
 
     pub fn oi_search_cosine(h: *mut oi_index, queries: *const f32, nq: u32, k: u32, out_ids: *mut u32, out_scores: *mut f32) -> oi_status;
     pub fn oi_search_bm25(h: *mut oi_index, q_terms: *const u32, q_offsets: *const u32, nq: u32, k: u32, out_ids: *mut u32,
@@ -82,6 +104,13 @@ extern "C" {
 
     pub fn oi_lexicon_analyze(device: i32, texts: *const u8, offsets: *const u64, n_posts: u64, out_polarity: *mut f64,
                               out_speculative: *mut u8, out_bull_hits: *mut u32, out_bear_hits: *mut u32) -> oi_status;
+
+    pub fn oi_lexicon_create(device: i32, reserve_bytes: u64, reserve_posts: u64, out: *mut *mut oi_lexicon) -> oi_status;
+    pub fn oi_lexicon_destroy(lx: *mut oi_lexicon);
+    pub fn oi_lexicon_run(lx: *mut oi_lexicon, texts: *const u8, offsets: *const u64, n_posts: u64, out_polarity: *mut f64,
+                          out_speculative: *mut u8, out_bull_hits: *mut u32, out_bear_hits: *mut u32, bull_bear_threshold: f64,
+                          out_summary: *mut oi_social_summary) -> oi_status;
+    pub fn oi_lexicon_launch_count(lx: *const oi_lexicon) -> u64;
 
     pub fn oi_index_launch_count(h: *const oi_index) -> u64;
     pub fn oi_index_set_option(h: *mut oi_index, name: *const c_char, value: i64) -> oi_status;

@@ -74,3 +74,38 @@ def test_large_batch_is_aligned_to_input_order(oi):
     for i in range(0, len(texts), 37):
         wp, ws, wb, we = O.lexicon_score(texts[i])
         assert (pol[i], bool(spec[i]), int(bull[i]), int(bear[i])) == (wp, ws, wb, we)
+
+
+def test_handle_api_and_fused_social_summary(oi, G):
+    """round 2: the handle form (persistent stream / buffers) returns what the one-shot call returns, and the fused
+    social summary equals the oracle's restatement of SpeculationEngine::social_summary (pinned to the reference's
+    fixture values: net 0.5, 7 / 2 / 1, speculation index 0.3, bull/bear 3.5) bit for bit."""
+    posts = [p["text"] for p in G["fixture_posts"]["posts"]] if "fixture_posts" in G else None
+    rnd = random.Random(11)
+    words = ["moon", "calls", "puts", "yolo", "dump", "rally", "the", "AAPL", "0dte", "x", "bagholder", "Ⅻ", "K", "İ"]
+    many = [" ".join(rnd.choice(words) for _ in range(rnd.randint(0, 40))) for _ in range(3000)]
+    with oi.GpuLexicon(reserve_bytes=64, reserve_posts=2) as lx:       # tiny reservation: the buffers must grow
+        for texts in ([t for t in (posts or [])], many, ["", "moon"], many[:7]):
+            if not texts:
+                continue
+            pol, spec, bull, bear, summ = lx.analyze(texts, summary=True)
+            p2, s2, b2, e2 = oi.lexicon_analyze(texts)
+            assert np.array_equal(pol, p2) and np.array_equal(spec, s2) and np.array_equal(bull, b2) and np.array_equal(bear, e2)
+            for i, t in enumerate(texts[:200]):
+                assert (pol[i], bool(spec[i]), int(bull[i]), int(bear[i])) == O.lexicon_score(t), repr(t)
+            want = O.social_summary(pol, spec.astype(np.int32))
+            for f in ("total", "bullish", "bearish", "neutral"):
+                assert summ[f] == want[f], f
+            for f in ("net_sentiment", "speculation_index", "bull_bear_ratio"):
+                assert np.float64(summ[f]).view(np.uint64) == np.float64(want[f]).view(np.uint64), f
+        assert lx.launch_count() >= 6
+        # a post longer than the shared-memory staging area takes the in-place path
+        long_post = " ".join(rnd.choice(words) for _ in range(3000))
+        assert len(long_post.encode()) > 4096
+        pol, spec, bull, bear = lx.analyze([long_post, "calls"])
+        assert (pol[0], bool(spec[0]), int(bull[0]), int(bear[0])) == O.lexicon_score(long_post)
+    if posts:
+        with oi.GpuLexicon() as lx:
+            _, _, _, _, summ = lx.analyze(posts, summary=True)
+        assert summ["total"] == 10 and (summ["bullish"], summ["bearish"], summ["neutral"]) == (7, 2, 1)
+        assert summ["net_sentiment"] == 0.5 and summ["speculation_index"] == 0.3 and summ["bull_bear_ratio"] == 3.5

@@ -67,7 +67,7 @@ def test_store_hybrid_matches_oracle(oi, tmp_path, n, vocab, dim, k):
     rows = store.normalise_rows_f32(emb)
     qn = store.normalise_rows_f32(qv)
     for j, text in enumerate(texts):
-        want_terms = [tid[t] for t in O.tokenize(text) if t in tid]
+        want_terms = list(dict.fromkeys(tid[t] for t in O.tokenize(text) if t in tid))  # de-duplicated, first-seen order
         assert [tid[x] for x in terms_words[j]] == want_terms
         cs = O.cosine_scores_f32(rows, qn[j])
         c_ids, c_sc, _ = O.topk_f64(cs, k)

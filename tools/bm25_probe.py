@@ -44,9 +44,11 @@ def pools(nq, uniform):
     return [bench._zipf_queries(nq, 8, cdf, 100 + p) for p in range(4)]
 
 
-out = {"lib": os.environ.get("OI_GPU_LIB", "in-tree"), "n_docs": args.docs}
-for nq in ((args.batch,) if args.once else (1024, 256)):
-    for uniform in ((False,) if args.once else (False, True)):
+if "OI_IPW" in os.environ:
+    opt("bm25_items_per_warp", int(os.environ["OI_IPW"]))
+out = {"lib": os.environ.get("OI_GPU_LIB", "in-tree"), "n_docs": args.docs, "ipw": os.environ.get("OI_IPW", "default")}
+for nq in ((args.batch,) if (args.once or "OI_IPW" in os.environ) else (1024, 256)):
+    for uniform in ((False,) if (args.once or "OI_IPW" in os.environ) else (False, True)):
         ps = pools(nq, uniform)
         d_t = [torch.from_numpy(p.astype(np.int32).reshape(-1)).to(dev) for p in ps]
         d_o = torch.arange(0, nq * 8 + 1, 8, dtype=torch.int32, device=dev)
