@@ -111,6 +111,15 @@ class ClockSampler:
                 "power_w_median": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _gemm_traffic(n_rows):
+    """dram bytes per main-pass launch, from the committed ncu capture (profiles/traffic.json), scaled by the row count"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["cosine_gemm_main_bf16_10Mx768_b256"]
+        return t["traffic_bytes_per_launch"] / t["algorithmic_bytes_per_launch"] * n_rows * DIM * 2
+    except Exception:
+        return None
+
+
 def _cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -278,9 +287,11 @@ def time_hybrid(ix, dev, cdf, dist, steps, warmup, rank, local_rank, sample_cloc
     if dist is not None:
         ix.set_option("comm_debug_skip_gather", 1)
     ids1, sc1 = d_out[0], d_rrf
-    ms_cos = allmax(_dev_time(lambda i: ix.search_cosine_dev(d_q[i % n_pool], BATCH, TOPK, ids1, sc1, stream), max(5, steps // 2), 2))
-    barrier()
+    # BM25 first: an issue-bound kernel timed right after the power-capped tensor-core leg looks up to 30 % slower than it
+    # is (the SM clock needs tens of milliseconds to recover; docs/NOTES_r01.md)
     ms_bm = allmax(_dev_time(lambda i: ix.search_bm25_dev(d_t[i % n_pool], d_offs, BATCH, TOPK, ids1, sc1, stream), max(5, steps // 2), 2))
+    barrier()
+    ms_cos = allmax(_dev_time(lambda i: ix.search_cosine_dev(d_q[i % n_pool], BATCH, TOPK, ids1, sc1, stream), max(5, steps // 2), 2))
     barrier()
     if dist is not None:
         ix.set_option("comm_debug_skip_gather", 0)
@@ -555,7 +566,8 @@ def main():
                     "timing": "wall clock around blocking oi_search_hybrid calls with pinned host buffers, max over ranks, median region"},
             "gpu_launches": res["launches"],
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
-                         "traffic": None, "kernel": "cosine_gemm_kernel (tcgen05; the step's dominant kernel)",
+                         "traffic": _gemm_traffic(n_local), "traffic_source": "static ncu --set full capture of the same kernel at 10M x 768, batch 256 (profiles/r02_ncu_cosine_gemm.md: DRAM read + write = 1.06 x the algorithmic bytes), scaled to this shard's rows; not measured in this run",
+                         "kernel": "cosine_gemm_kernel (tcgen05; the step's dominant kernel)",
                          "peak_source": peaks["source"] + ", bf16_tflops_sustained: the kernel is timed inside a long back-to-back loop under the power cap",
                          "frac_of_burst_peak": tf / peaks["bf16_tflops"], "flops_per_launch": flops,
                          "hbm_gbs": gbs, "hbm_frac_of_measured_copy": gbs / peaks["hbm_gbs"], "bytes_per_launch": n_local * DIM * 2,

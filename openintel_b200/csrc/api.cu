@@ -73,6 +73,40 @@ static cudaError_t call_end(oi_index *h, cudaStream_t st) {
   return e;
 }
 
+// A staging slot for one small host-buffer call.  Taken under the handle's lock (waiting, lock released, while all are
+// busy); given back by the guard after the caller has copied its results out -- or on any early return.
+struct SlotLease {
+  oi_index *h;
+  std::unique_lock<std::mutex> &lock;
+  oi_index::Slot *sl;
+  SlotLease(oi_index *h_, std::unique_lock<std::mutex> &lock_) : h(h_), lock(lock_), sl(nullptr) {
+    for (;;) {
+      for (oi_index::Slot &c : h->slots)
+        if (!c.busy) { sl = &c; break; }
+      if (sl) break;
+      h->slot_cv.wait(lock);
+    }
+    sl->busy = true;
+  }
+  ~SlotLease() {
+    if (!lock.owns_lock()) lock.lock();
+    sl->busy = false;
+    h->slot_cv.notify_one();
+  }
+  // the enqueue is complete: record the slot's event, let the next caller in, wait for this call's results
+  oi_status finish(cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(sl->done, st);
+    if (e == cudaSuccess) e = call_end(h, st);
+    if (e == cudaSuccess) {
+      lock.unlock();
+      e = cudaEventSynchronize(sl->done);
+      if (e != cudaSuccess) lock.lock();
+    }
+    if (e != cudaSuccess) return h->fail(OI_ERR_CUDA, "host-buffer call failed: %s", cudaGetErrorString(e));
+    return OI_OK;
+  }
+};
+
 extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) {
   if (!out) return create_fail(OI_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
@@ -133,10 +167,13 @@ extern "C" oi_status oi_index_create(const oi_index_desc *desc, oi_index **out) 
   if ((e = cudaMalloc(&h->d_keys_bm25, B * K * sizeof(u64))) != cudaSuccess) return bail("cudaMalloc(keys)", e);
   if ((e = cudaMalloc(&h->d_out_u32, 3 * B * K * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(out)", e);
   if ((e = cudaMalloc(&h->d_out_f32, B * K * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(out)", e);
-  if ((e = cudaHostAlloc(&h->h_pin_in, OI_PIN_BYTES, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
-  if ((e = cudaHostAlloc(&h->h_pin_out, OI_PIN_BYTES, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
-  if ((e = cudaMalloc(&h->d_pin_in, OI_PIN_BYTES)) != cudaSuccess) return bail("cudaMalloc(staging)", e);
-  if ((e = cudaMalloc(&h->d_pin_out, OI_PIN_BYTES)) != cudaSuccess) return bail("cudaMalloc(staging)", e);
+  for (oi_index::Slot &sl : h->slots) {
+    if ((e = cudaHostAlloc(&sl.h_in, OI_PIN_BYTES, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc(&sl.h_out, OI_PIN_BYTES, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaMalloc(&sl.d_in, OI_PIN_BYTES)) != cudaSuccess) return bail("cudaMalloc(staging)", e);
+    if ((e = cudaMalloc(&sl.d_out, OI_PIN_BYTES)) != cudaSuccess) return bail("cudaMalloc(staging)", e);
+    if ((e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  }
   *out = h;
   return OI_OK;
 }
@@ -161,10 +198,13 @@ extern "C" void oi_index_destroy(oi_index *h) {
   cudaFree(h->d_out_u32);
   cudaFree(h->d_out_f32);
   cudaFree(h->d_gather);
-  cudaFree(h->d_pin_in);
-  cudaFree(h->d_pin_out);
-  cudaFreeHost(h->h_pin_in);
-  cudaFreeHost(h->h_pin_out);
+  for (oi_index::Slot &sl : h->slots) {
+    cudaFree(sl.d_in);
+    cudaFree(sl.d_out);
+    cudaFreeHost(sl.h_in);
+    cudaFreeHost(sl.h_out);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   if (h->ev_last) cudaEventDestroy(h->ev_last);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -398,7 +438,7 @@ extern "C" oi_status oi_search_cosine_dev(oi_index *h, const float *d_queries, u
 extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_t nq, uint32_t k,
                                       uint32_t *out_ids, float *out_scores) {
   if (!h) return OI_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::unique_lock<std::mutex> lock(h->mu);
   oi_status s = check_search_args(h, nq, k);
   if (s) return s;
   OI_REQUIRE(nq == 0 || (queries && out_ids && out_scores), "NULL host pointer");
@@ -408,17 +448,18 @@ extern "C" oi_status oi_search_cosine(oi_index *h, const float *queries, uint32_
   OI_CK(call_begin(h, st));
   const size_t qbytes = (size_t)nq * h->desc.dim * sizeof(float), n = (size_t)nq * k;
   if (!h->no_pinned_staging && qbytes <= OI_PIN_BYTES && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
-    memcpy(h->h_pin_in, queries, qbytes);
-    OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, qbytes, cudaMemcpyHostToDevice, st));
-    if ((s = cosine_keys(h, reinterpret_cast<const float *>(h->d_pin_in), nq, k, st))) return s;
-    uint32_t *d_ids = reinterpret_cast<uint32_t *>(h->d_pin_out);
-    float *d_sc = reinterpret_cast<float *>(h->d_pin_out + n * 4);
+    SlotLease lease(h, lock);
+    oi_index::Slot *sl = lease.sl;
+    memcpy(sl->h_in, queries, qbytes);
+    OI_CK(cudaMemcpyAsync(sl->d_in, sl->h_in, qbytes, cudaMemcpyHostToDevice, st));
+    if ((s = cosine_keys(h, reinterpret_cast<const float *>(sl->d_in), nq, k, st))) return s;
+    uint32_t *d_ids = reinterpret_cast<uint32_t *>(sl->d_out);
+    float *d_sc = reinterpret_cast<float *>(sl->d_out + n * 4);
     OI_CK(oi_launch_unpack_keys(h->d_keys_cos, nq * k, d_ids, d_sc, st, &h->launches));
-    OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 8, cudaMemcpyDeviceToHost, st));
-    OI_CK(call_end(h, st));
-    OI_CK(cudaStreamSynchronize(st));
-    memcpy(out_ids, h->h_pin_out, n * 4);
-    memcpy(out_scores, h->h_pin_out + n * 4, n * 4);
+    OI_CK(cudaMemcpyAsync(sl->h_out, sl->d_out, n * 8, cudaMemcpyDeviceToHost, st));
+    if ((s = lease.finish(st))) return s;
+    memcpy(out_ids, sl->h_out, n * 4);
+    memcpy(out_scores, sl->h_out + n * 4, n * 4);
     return OI_OK;
   }
   OI_CK(cudaMemcpyAsync(h->d_queries, queries, qbytes, cudaMemcpyHostToDevice, st));
@@ -519,7 +560,7 @@ extern "C" oi_status oi_search_bm25_dev(oi_index *h, const uint32_t *d_q_terms, 
 extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const uint32_t *q_offsets, uint32_t nq,
                                     uint32_t k, uint32_t *out_ids, float *out_scores) {
   if (!h) return OI_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::unique_lock<std::mutex> lock(h->mu);
   oi_status s = check_search_args(h, nq, k);
   if (s) return s;
   if (nq == 0) return OI_OK;
@@ -532,16 +573,17 @@ extern "C" oi_status oi_search_bm25(oi_index *h, const uint32_t *q_terms, const 
   size_t o_offs, o_terms;
   const size_t in_bytes = pin_in_layout(0, nq, q_offsets[nq], &o_offs, &o_terms);
   if (!h->no_pinned_staging && in_bytes && n * 8 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
-    memcpy(h->h_pin_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
-    if (q_offsets[nq]) memcpy(h->h_pin_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);
-    OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, in_bytes, cudaMemcpyHostToDevice, st));
-    if ((s = bm25_keys(h, reinterpret_cast<const uint32_t *>(h->d_pin_in + o_terms), reinterpret_cast<const uint32_t *>(h->d_pin_in + o_offs), nq, k, st))) return s;
-    OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, reinterpret_cast<uint32_t *>(h->d_pin_out), reinterpret_cast<float *>(h->d_pin_out + n * 4), st, &h->launches));
-    OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 8, cudaMemcpyDeviceToHost, st));
-    OI_CK(call_end(h, st));
-    OI_CK(cudaStreamSynchronize(st));
-    memcpy(out_ids, h->h_pin_out, n * 4);
-    memcpy(out_scores, h->h_pin_out + n * 4, n * 4);
+    SlotLease lease(h, lock);
+    oi_index::Slot *sl = lease.sl;
+    memcpy(sl->h_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
+    if (q_offsets[nq]) memcpy(sl->h_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);
+    OI_CK(cudaMemcpyAsync(sl->d_in, sl->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    if ((s = bm25_keys(h, reinterpret_cast<const uint32_t *>(sl->d_in + o_terms), reinterpret_cast<const uint32_t *>(sl->d_in + o_offs), nq, k, st))) return s;
+    OI_CK(oi_launch_unpack_keys(h->d_keys_bm25, nq * k, reinterpret_cast<uint32_t *>(sl->d_out), reinterpret_cast<float *>(sl->d_out + n * 4), st, &h->launches));
+    OI_CK(cudaMemcpyAsync(sl->h_out, sl->d_out, n * 8, cudaMemcpyDeviceToHost, st));
+    if ((s = lease.finish(st))) return s;
+    memcpy(out_ids, sl->h_out, n * 4);
+    memcpy(out_scores, sl->h_out + n * 4, n * 4);
     return OI_OK;
   }
   if ((s = stage_terms(h, q_terms, q_offsets, nq, st))) return s;
@@ -621,7 +663,7 @@ extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const u
                                       uint32_t nq, uint32_t k, uint32_t rrf_k, uint32_t *out_ids, float *out_rrf,
                                       uint32_t *out_rank_cos, uint32_t *out_rank_bm25) {
   if (!h) return OI_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::unique_lock<std::mutex> lock(h->mu);
   oi_status s = check_search_args(h, nq, k);
   if (s) return s;
   OI_REQUIRE(rrf_k >= 1 && rrf_k <= 1000000, "rrf_k = %u outside 1..1e6", rrf_k);
@@ -636,22 +678,23 @@ extern "C" oi_status oi_search_hybrid(oi_index *h, const float *queries, const u
   size_t o_offs, o_terms;
   const size_t in_bytes = pin_in_layout(qbytes, nq, q_offsets[nq], &o_offs, &o_terms);
   if (!h->no_pinned_staging && in_bytes && n * 16 <= OI_PIN_BYTES) {  // small call: one pinned copy each way
-    memcpy(h->h_pin_in, queries, qbytes);
-    memcpy(h->h_pin_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
-    if (q_offsets[nq]) memcpy(h->h_pin_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);
-    OI_CK(cudaMemcpyAsync(h->d_pin_in, h->h_pin_in, in_bytes, cudaMemcpyHostToDevice, st));
-    uint32_t *d_ids = reinterpret_cast<uint32_t *>(h->d_pin_out), *d_rc = d_ids + 2 * n, *d_rb = d_ids + 3 * n;
+    SlotLease lease(h, lock);
+    oi_index::Slot *sl = lease.sl;
+    memcpy(sl->h_in, queries, qbytes);
+    memcpy(sl->h_in + o_offs, q_offsets, ((size_t)nq + 1) * 4);
+    if (q_offsets[nq]) memcpy(sl->h_in + o_terms, q_terms, (size_t)q_offsets[nq] * 4);
+    OI_CK(cudaMemcpyAsync(sl->d_in, sl->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    uint32_t *d_ids = reinterpret_cast<uint32_t *>(sl->d_out), *d_rc = d_ids + 2 * n, *d_rb = d_ids + 3 * n;
     float *d_rrf = reinterpret_cast<float *>(d_ids + n);
-    if ((s = hybrid_enqueue(h, reinterpret_cast<const float *>(h->d_pin_in), reinterpret_cast<const uint32_t *>(h->d_pin_in + o_terms),
-                            reinterpret_cast<const uint32_t *>(h->d_pin_in + o_offs), nq, k, rrf_k, d_ids, d_rrf, d_rc, d_rb, st)))
+    if ((s = hybrid_enqueue(h, reinterpret_cast<const float *>(sl->d_in), reinterpret_cast<const uint32_t *>(sl->d_in + o_terms),
+                            reinterpret_cast<const uint32_t *>(sl->d_in + o_offs), nq, k, rrf_k, d_ids, d_rrf, d_rc, d_rb, st)))
       return s;
-    OI_CK(cudaMemcpyAsync(h->h_pin_out, h->d_pin_out, n * 16, cudaMemcpyDeviceToHost, st));
-    OI_CK(call_end(h, st));
-    OI_CK(cudaStreamSynchronize(st));
-    memcpy(out_ids, h->h_pin_out, n * 4);
-    memcpy(out_rrf, h->h_pin_out + n * 4, n * 4);
-    memcpy(out_rank_cos, h->h_pin_out + n * 8, n * 4);
-    memcpy(out_rank_bm25, h->h_pin_out + n * 12, n * 4);
+    OI_CK(cudaMemcpyAsync(sl->h_out, sl->d_out, n * 16, cudaMemcpyDeviceToHost, st));
+    if ((s = lease.finish(st))) return s;
+    memcpy(out_ids, sl->h_out, n * 4);
+    memcpy(out_rrf, sl->h_out + n * 4, n * 4);
+    memcpy(out_rank_cos, sl->h_out + n * 8, n * 4);
+    memcpy(out_rank_bm25, sl->h_out + n * 12, n * 4);
     return OI_OK;
   }
   OI_CK(cudaMemcpyAsync(h->d_queries, queries, qbytes, cudaMemcpyHostToDevice, st));

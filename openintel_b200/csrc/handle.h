@@ -7,6 +7,7 @@ struct OiComm;  // comm.cu
 struct OiGemm;  // cosine_gemm.cu
 
 #define OI_PIN_BYTES (1u << 20)
+#define OI_SLOTS 4
 
 struct oi_index {
   oi_index_desc desc{};
@@ -49,8 +50,18 @@ struct oi_index {
   float *d_out_f32 = nullptr;     // [max_batch][max_k]
   // small host-buffer calls go through one pinned staging block each way: one H2D copy of (queries | terms |
   // offsets) and one D2H copy of (ids | scores | ranks) instead of 3 + 4 copies from / to pageable memory
-  unsigned char *h_pin_in = nullptr, *h_pin_out = nullptr;  // OI_PIN_BYTES each (cudaHostAlloc)
-  unsigned char *d_pin_in = nullptr, *d_pin_out = nullptr;  // device mirrors
+  // ... and there are OI_SLOTS such blocks: a host-buffer call owns one from its enqueue until it has copied its results
+  // out, and the handle's lock is only held for the ENQUEUE -- while one thread waits for its results another one
+  // already packs and enqueues the next call behind it on the stream (the reference awaits one &self from many tasks:
+  // src/application/analyze.rs:30-37).  The kernels of the calls still run one after the other (one set of workspaces).
+  struct Slot {
+    unsigned char *h_in = nullptr, *h_out = nullptr;  // OI_PIN_BYTES each (cudaHostAlloc)
+    unsigned char *d_in = nullptr, *d_out = nullptr;  // device mirrors
+    cudaEvent_t done = nullptr;                       // recorded behind the call's last copy
+    bool busy = false;
+  };
+  Slot slots[4];
+  std::condition_variable slot_cv;
   int no_pinned_staging = 0;  // tests: take the large-call path (direct copies from / to the caller's buffers)
 
   // batched cosine on the tensor cores (cosine_gemm.cu); workspace is created on first use
@@ -62,7 +73,7 @@ struct oi_index {
   int gemm_sample_tiles = 0;   // probe-pass tiles per CTA override (0 = default: 1/128 of the CTA's tiles); > 0 also forces the probe on small shards
   bool gemm_force_lite = false;  // experiments: always the 96 KB-ring kernel
   int gemm_pair = 0;           // 1: an even number of query tiles runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256); measured 5 % slower
-                               // than two independent M = 128 CTAs (profiles/r02_gemm_notes.md), so it is opt-in
+                               // than two independent M = 128 CTAs (profiles/r02_gemm_ab.md), so it is opt-in
   int gemm_pair_ring = 48;     // slabs (4 KB) in a pair CTA's ring at dim 768: 24 (96 KB) or 48 (192 KB)
 
   // BM25

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <condition_variable>
 #include <mutex>
 #include <string>
 

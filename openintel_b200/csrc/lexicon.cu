@@ -51,6 +51,15 @@ __constant__ Word c_jargon[N_JARGON] = {pack_word("calls"), pack_word("puts"), p
                                         pack_word("squeeze"), pack_word("otm"), pack_word("itm"), pack_word("strike"),
                                         pack_word("iv"), pack_word("delta"), pack_word("vega"), pack_word("contracts")};
 
+// The 39 distinct list words in a 128-slot perfect hash (the multiplier was searched offline: no two words share a slot),
+// built in shared memory at kernel start from the tables above: a token costs one multiply, one table read and one
+// 128-bit compare instead of 42 compares (ncu, round 1 layout: 9.2 G warp instructions for 300 MB of text).
+struct LexSlot { unsigned long long lo, hi; uint32_t flags, pad; };  // flags: 1 = BULL, 2 = BEAR, 4 = JARGON
+constexpr int kLexSlots = 128;
+__host__ __device__ __forceinline__ uint32_t lex_hash(unsigned long long lo, unsigned long long hi) {
+  return (uint32_t)(((lo ^ (hi * 0x9E3779B97F4A7C15ull)) * 0x3CDFA3C5131A5AF7ull) >> 57);
+}
+
 enum { CLS_SEP = 0, CLS_SKIP = -1, CLS_I_THEN_SEP = -2 };  // > 0: a token byte (the lowered char)
 
 // class of byte position i of text[0..len): token char (> 0), separator, transparent, or the
@@ -75,6 +84,18 @@ __global__ void __launch_bounds__(256) lexicon_kernel(const uint8_t *texts, cons
                                                       unsigned long long n_posts, double *polarity,
                                                       uint8_t *speculative, uint32_t *bull_hits, uint32_t *bear_hits) {
   __shared__ __align__(16) uint8_t s_stage[8][kStageBytes + 32];
+  __shared__ LexSlot s_tab[kLexSlots];
+  if (threadIdx.x < kLexSlots) s_tab[threadIdx.x] = LexSlot{0ull, 0ull, 0u, 0u};
+  __syncthreads();
+  if (threadIdx.x < N_BULL + N_BEAR + N_JARGON) {
+    const int w = threadIdx.x;
+    const Word wd = w < N_BULL ? c_bull[w] : (w < N_BULL + N_BEAR ? c_bear[w - N_BULL] : c_jargon[w - N_BULL - N_BEAR]);
+    LexSlot *e = &s_tab[lex_hash(wd.lo, wd.hi)];
+    e->lo = wd.lo;  // a word that is in two lists writes the same key twice
+    e->hi = wd.hi;
+    atomicOr(&e->flags, w < N_BULL ? 1u : (w < N_BULL + N_BEAR ? 2u : 4u));
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -122,12 +143,11 @@ __global__ void __launch_bounds__(256) lexicon_kernel(const uint8_t *texts, cons
       }
       const bool too_long = n > 16;
       if (too_long) continue;
-#pragma unroll
-      for (int w = 0; w < N_BULL; ++w) bull += (c_bull[w].lo == lo && c_bull[w].hi == hi);
-#pragma unroll
-      for (int w = 0; w < N_BEAR; ++w) bear += (c_bear[w].lo == lo && c_bear[w].hi == hi);
-#pragma unroll
-      for (int w = 0; w < N_JARGON; ++w) spec |= (c_jargon[w].lo == lo && c_jargon[w].hi == hi);
+      const LexSlot e = s_tab[lex_hash(lo, hi)];
+      const uint32_t f = (e.lo == lo && e.hi == hi) ? e.flags : 0u;
+      bull += f & 1u;
+      bear += (f >> 1) & 1u;
+      spec |= (f >> 2) & 1u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
