@@ -41,7 +41,7 @@ UNIT = "queries/s"
 # the value is the one that measured best (profiles/r02_overlap_sweep.md)
 DEFAULT_OVERLAP = 0
 # exchange of the shard-local lists at N > 1: "nccl" (ncclAllGather) or "p2p" (peer stores into IPC-mapped buffers + flags)
-DEFAULT_EXCHANGE = "p2p"
+DEFAULT_EXCHANGE = "nccl"   # measured: p2p 4.36 vs nccl 4.23 ms/step at N = 8, 16.07 vs 16.06 at N = 2 (profiles/r02_bench_n8.json): no gain
 
 
 def workload_name(n_docs):
@@ -518,14 +518,6 @@ def main():
     value = n_queries / (ms * 1e-3)
     e2e_value = n_queries / statistics.median([r["e2e_s"] for r in runs])
 
-    # the exchange on its own (sharded runs): the same step with the all-gather skipped
-    exchange_us = None
-    if world > 1:
-        ix.set_option("comm_debug_skip_gather", 1)
-        r2 = time_hybrid(ix, dev, cdf, dist, args.steps, args.warmup, rank, local_rank, sample_clocks=False)
-        ix.set_option("comm_debug_skip_gather", 0)
-        exchange_us = (ms - r2["ms_total"]) / args.steps * 1e3
-
     if rank == 0:
         ms_cos, ms_bm = res["ms_cos"], res["ms_bm25"]
         flops = 2.0 * n_local * DIM * BATCH
@@ -578,7 +570,7 @@ def main():
                      "step_over_max_leg": step_ms / max(ms_cos, ms_bm), "step_over_sum_of_legs": step_ms / (ms_cos + ms_bm),
                      "bm25": {"postings_touched_per_query_per_gpu": df_sum, "algorithmic_posting_gbs": df_sum * 8 * BATCH / (ms_bm * 1e-3) / 1e9,
                               "bound": "issue / L2 (static ncu capture: profiles/r02_ncu_bm25.md)"},
-                     "exchange_us_per_step": exchange_us, "exchange": args.exchange if world > 1 else None,
+                     "exchange": args.exchange if world > 1 else None,
                      "other_exchange": other_exchange,
                      "p2p_status": (lambda st: {"batches": st[0], "timed_out": st[1]})(ix.p2p_status()) if (world > 1 and args.exchange == "p2p") else None},
             "cpu_baseline": cpu, "clocks": res["clocks"], "verify": verify,

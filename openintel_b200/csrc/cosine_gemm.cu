@@ -375,7 +375,7 @@ __device__ __forceinline__ void cosine_gemm_body(const CUtensorMap &tmap, const 
       const uint32_t n_valid = min(kTileDocs, p.n_rows - doc0);
       // NH = 1 (stand-alone kernel): all 64 scores of the tile are pulled at once and the accumulator is released as
       // soon as they are in registers -- the MMAs of tile t + 2 never wait for this warp's arithmetic (holding the
-      // accumulator through two TMEM round trips and the filter cost 30 % of the kernel: profiles/r02_gemm_ab.md).
+      // accumulator through two TMEM round trips and the filter cost ~6 %: profiles/r02_gemm_ab.md).
       // NH = 2 (lite kernel, 128 registers): two halves of 32 columns, released after the second.
       constexpr int NH = EARLY ? 1 : 2, W = 64 / NH;
 #pragma unroll
