@@ -1,5 +1,6 @@
 // oi_synth.cuh — the SPEC §9 counter hash, host+device.  Must stay bit-identical to
-// oracle/oracle.c (tests/test_gpu_synth.py compares generated rows bit for bit).
+// oracle/oracle.c (tests/test_gpu_cosine.py::test_device_synth_is_bit_identical_to_oracle and
+// tests/test_gpu_bm25.py::test_device_synth_csr_is_bit_identical_to_oracle compare the output bit for bit).
 #pragma once
 #include <stdint.h>
 
