@@ -21,11 +21,13 @@
 //     first pass only stores, so the block is never cleared.
 //   * after the last term the warp scans acc[] once: every positive score whose key beats the
 //     running threshold goes to the warp's candidate buffer (filter + buffer selection, the same
-//     scheme as the cosine scan), and the k-th best key is published grid-wide (atomicMax) so later
-//     blocks of the same query filter harder.  A block scanned without any threshold takes the k-th
-//     largest of its 256 group maxima as a bound first.
+//     scheme as the cosine scan).  A block scanned without any threshold takes the k-th largest of its
+//     256 group maxima as a bound first.  The scan is SKIPPED when the threshold exceeds what the
+//     query's dense terms can give and no sparse posting of the block produced a score that reaches it.
 //   * the item ends with a sorted k-list per (query, super-range); bm25 merge = one CTA per
-//     query over the S lists.
+//     query over the S lists.  A finished item also folds its list into the query's running best-k
+//     (per-query try-lock); the k-th key of that list is the grid-wide threshold, so later items of
+//     the query filter with the best k of everything scored so far, not of one super-range.
 //
 //   algorithmic bytes per query = postings touched x 8 B (doc id + folded weight)
 #include <cub/device/device_radix_sort.cuh>
@@ -54,6 +56,7 @@ struct OiBm25 {
   uint2 *d_post = nullptr;        // [P + 68] interleaved (doc id, weight bits): what the scoring kernel streams
   float *d_dense = nullptr;       // [n_dense][dense_stride] weight columns of the densest terms
   int *d_dense_slot = nullptr;    // [n_terms] column index or -1
+  float *d_dense_max = nullptr;   // [32] largest weight of each dense column
   uint32_t n_dense = 0, dense_stride = 0;
   bool finalized = false;
   bool attr_set = false;          // dynamic shared-memory limit of the scoring kernels raised
@@ -64,6 +67,8 @@ struct OiBm25 {
   uint32_t *d_counter = nullptr;  // item counter
   u64 *d_lists = nullptr;         // [S][nq][k]
   size_t lists_cap = 0;           // in keys
+  u64 *d_best = nullptr;          // [max_batch][max_k] running best k per query (threshold accelerator)
+  uint32_t *d_qlock = nullptr;    // [max_batch] try-lock of d_best[q]
   uint32_t *d_in_terms = nullptr; // staging of the host call's flat term array [max_batch * 64]
   uint32_t *d_in_offs = nullptr;  // [max_batch + 1]
 };
@@ -138,12 +143,15 @@ struct Bm25Params {
   const uint2 *post;          // [P + 68] interleaved (doc id, folded weight bits)
   const float *dense;         // [n_dense][dense_stride] weight columns of the densest terms (0 where absent)
   const int *dense_slot;      // [n_terms] column of a term, or -1
+  const float *dense_max;     // [n_dense] largest weight of each column (selection skip, see the kernel)
   uint32_t dense_stride;
   const uint32_t *qterms;     // [nq][64]
   const uint32_t *qnt;        // [nq]
   u64 *gthr;                  // [nq]
   uint32_t *counter;
   u64 *lists;                 // [S][nq][k]
+  u64 *best;                  // [nq][k] running best k of each query's finished items (threshold accelerator; zeroed by prep)
+  uint32_t *qlock;            // [nq] one try-lock per query for folding an item into best[]
   uint32_t n_docs, doc_base, nq, k;
   uint32_t cap;               // candidate buffer keys per warp (power of two, >= 2k)
   uint32_t R;                 // docs per block (a power of two)
@@ -168,7 +176,7 @@ __device__ __forceinline__ uint4 ldg_post2(const uint2 *p) {
 // a bulk copy of the 512 bytes from exactly the address the first iteration would load.
 __device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 base, uint32_t pos, uint32_t end, uint32_t bbase,
                                             uint32_t bend, float *acc, int lane, const uint4 *st, uint32_t *pos_out,
-                                            uint32_t *nxt_out) {
+                                            uint32_t *nxt_out, float &mx) {
   // list-local 32-bit slot numbers over a 16-byte-aligned view of the list: slot j = posting (j - par)
   const uint32_t par = (uint32_t)(base & 1ull);
   const uint2 *lp = post + (base - par);
@@ -186,11 +194,15 @@ __device__ __forceinline__ void sparse_pass(const uint2 *__restrict__ post, u64 
     const bool in0 = v.x < bend, in1 = v.z < bend;
     if (in0) {
       float *x = acc + (v.x - bbase);
-      *x = *x + __uint_as_float(v.y);  // SPEC §3: one f32 add, previous terms first
+      const float nx = *x + __uint_as_float(v.y);  // SPEC §3: one f32 add, previous terms first
+      *x = nx;
+      mx = fmaxf(mx, nx);
     }
     if (in1) {
       float *x = acc + (v.z - bbase);
-      *x = *x + __uint_as_float(v.w);
+      const float nx = *x + __uint_as_float(v.w);
+      *x = nx;
+      mx = fmaxf(mx, nx);
     }
     const uint32_t n = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in0)) + (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in1));
     applied += n;
@@ -252,77 +264,106 @@ __device__ __forceinline__ void bm25_bulk_g2s(void *smem_dst, const void *gmem_s
                : "memory");
 }
 
-// The term passes of one block for one register set, ascending term id (SPEC §3 order).  First every sparse list
-// with postings in the block gets its first 64-posting chunk requested -- lane i issues ONE bulk copy for term i,
-// all lists in flight at once, completion counted on the warp's mbarrier -- then the present lists are visited
-// in order: a dense term adds its column, a sparse term consumes its staged chunk (and, for a segment longer than
-// the chunk, goes on with direct loads).
+// Two IEEE f32 additions in one instruction (add.rn.f32x2, SASS FADD2): bit for bit what two add.rn.f32 give, half
+// the issue slots of the dense sweeps.
+__device__ __forceinline__ void add2(float &a0, float &a1, float b0, float b1) {
+  unsigned long long x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(x));
+}
+__device__ __forceinline__ void add4(float4 &a, const float4 &b) {
+  add2(a.x, a.y, b.x, b.y);
+  add2(a.z, a.w, b.z, b.w);
+}
+
 // One or two dense columns in one sweep over the block's scores: x = (FRESH ? 0 : acc) + a (+ b), ascending term
-// order, 4 x 128 bits per column and lane in flight.  FRESH = no pass has written acc[] for this block yet: the
+// order, software-pipelined in stages of 2 x 128 bits per column and lane.  FRESH = no pass has written acc[] for this block yet: the
 // sweep then only stores (0.0f + w == w for every weight, bit for bit), so the block needs no clearing pass.
 template <bool FRESH, int NC>
+__device__ __forceinline__ void dense_stage_load(const float4 *__restrict__ c0, const float4 *__restrict__ c1, uint32_t j, int lane, float4 (&va)[2],
+                                                 float4 (&vb)[2]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    va[u] = __ldg(c0 + j + 32 * u + lane);
+    if (NC == 2) vb[u] = __ldg(c1 + j + 32 * u + lane);
+  }
+}
+template <bool FRESH, int NC>
+__device__ __forceinline__ void dense_stage_apply(float4 *a4, uint32_t j, int lane, const float4 (&va)[2], const float4 (&vb)[2]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    float4 x = va[u];
+    if (!FRESH) {
+      float4 o = a4[j + 32 * u + lane];
+      add4(o, x);  // o + x: the earlier terms' sum first
+      x = o;
+    }
+    if (NC == 2) add4(x, vb[u]);
+    a4[j + 32 * u + lane] = x;
+  }
+}
+
+template <bool FRESH, int NC>
 __device__ __forceinline__ void dense_sweep(const float4 *__restrict__ c0, const float4 *__restrict__ c1, float4 *a4, uint32_t R, int lane) {
-#pragma unroll 2
+  // software pipeline over stages of 2 x 128 bits per column and lane: the loads of stage t + 1 are in flight while
+  // stage t is added and stored, so a sweep exposes one L2 latency instead of one per group of loads
+  float4 va0[2], vb0[2], va1[2], vb1[2];
+  dense_stage_load<FRESH, NC>(c0, c1, 0, lane, va0, vb0);
   for (uint32_t j0 = 0; j0 < R / 4; j0 += 128) {
-    float4 va[4], vb[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      va[u] = __ldg(c0 + j0 + 32 * u + lane);
-      if (NC == 2) vb[u] = __ldg(c1 + j0 + 32 * u + lane);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float4 x = va[u];
-      if (!FRESH) {
-        const float4 o = a4[j0 + 32 * u + lane];
-        x.x = o.x + x.x; x.y = o.y + x.y; x.z = o.z + x.z; x.w = o.w + x.w;
-      }
-      if (NC == 2) { x.x = x.x + vb[u].x; x.y = x.y + vb[u].y; x.z = x.z + vb[u].z; x.w = x.w + vb[u].w; }
-      a4[j0 + 32 * u + lane] = x;
-    }
+    dense_stage_load<FRESH, NC>(c0, c1, j0 + 64, lane, va1, vb1);
+    dense_stage_apply<FRESH, NC>(a4, j0, lane, va0, vb0);
+    if (j0 + 128 < R / 4) dense_stage_load<FRESH, NC>(c0, c1, j0 + 128, lane, va0, vb0);
+    dense_stage_apply<FRESH, NC>(a4, j0 + 64, lane, va1, vb1);
   }
 }
 
 // The term passes of one block for one register set, ascending term id (SPEC §3 order).  First every sparse list
 // with postings in the block gets its first 64-posting chunk requested -- lane i issues ONE bulk copy for term i,
 // all lists in flight at once, completion counted on the warp's mbarrier -- then the present lists are visited
-// in order: dense terms add their columns (two consecutive ones share a sweep), a sparse term consumes its staged
-// chunk (and, for a segment longer than the chunk, goes on with direct loads).  `fresh` = acc[] holds nothing for
-// this block yet: a dense first pass overwrites it, a sparse first pass clears it first.  `touched` accumulates an
-// upper bound of the documents with a positive score (postings applied; R per dense sweep).
+// in order: dense terms add their columns (two consecutive ones share a sweep), a sparse term consumes its chunk
+// (staged, or loaded directly when the warp's staging slots are taken) with ONE shuffle of set-up -- the owner lane
+// packs "postings left in the list from the chunk's first slot" and the 0/1 leading slot below the cursor into one
+// word -- and only a segment longer than the chunk fetches the rest of the list's registers and goes on with the
+// general loop (sparse_pass).  `fresh` = acc[] holds nothing for this block yet: a dense first pass overwrites it, a
+// sparse first pass clears it first.  `touched` accumulates an upper bound of the documents with a positive score
+// (postings applied; R per dense sweep); `mx` = per lane, the largest score a sparse posting produced.
 template <uint32_t RT>
-__device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, float *acc, uint4 *stage, void *mbar, uint32_t &phase,
-                                             bool &fresh, uint32_t &touched, uint32_t bbase, uint32_t bend, int lane) {
+__device__ __forceinline__ void block_passes(TermRegs &T, uint32_t dmask, const Bm25Params &p, float *acc, uint4 *stage, void *mbar,
+                                             uint32_t &phase, bool &fresh, uint32_t &touched, float &mx, uint32_t bbase, uint32_t bend,
+                                             int lane) {
   const uint32_t R = RT ? RT : p.R;
-  const bool present = T.nxt < bend;
-  const uint32_t pm = __ballot_sync(0xFFFFFFFFu, present);
+  const uint32_t pm = __ballot_sync(0xFFFFFFFFu, T.nxt < bend);
   if (pm == 0) return;
-  const uint32_t sm = __ballot_sync(0xFFFFFFFFu, present && T.den == OI_BM25_NONE);
-  const uint32_t n_sparse = (uint32_t)__popc(sm);
-  const uint32_t n_staged = min(n_sparse, p.nslot);
+  const uint32_t sm = pm & ~dmask;
+  // chunk geometry of this lane's list: 16-byte-aligned pair at or below the cursor
+  const uint32_t par = (uint32_t)(T.base & 1ull);
+  const uint32_t ca = (T.cur + par) & ~1u;
+  const u64 coff = (T.base - par) + ca;                                   // posting-array index of the chunk's slot 0
+  const uint32_t meta = (min(T.end + par - ca, 1u << 20) << 1) | ((T.cur + par) - ca);  // (slots left << 1) | leading slot
+  const uint32_t n_staged = min((uint32_t)__popc(sm), p.nslot);
   if (n_staged) {
     if (lane == 0) oi_mbar_expect_tx(mbar, n_staged * 512u);
     const uint32_t my_slot = (uint32_t)__popc(sm & ((1u << lane) - 1u));
-    if (((sm >> lane) & 1u) && my_slot < p.nslot) {
-      const uint32_t par = (uint32_t)(T.base & 1ull);
-      const uint32_t a = (T.cur + par) & ~1u;  // the 16-byte-aligned pair sparse_pass's first load starts from
-      bm25_bulk_g2s(stage + my_slot * 32u, p.post + (T.base - par) + a, 512u, mbar);  // the array is padded by 64 postings
-    }
+    if (((sm >> lane) & 1u) && my_slot < p.nslot)
+      bm25_bulk_g2s(stage + my_slot * 32u, p.post + coff, 512u, mbar);  // the array is padded by 64 postings
   }
   float4 *a4 = reinterpret_cast<float4 *>(acc);
   const uint32_t nxt_dense = bend < p.n_docs ? bend : OI_BM25_NONE;  // a dense term is present in every block
   bool waited = false;
   uint32_t m = pm;
+  uint32_t slot = 0;  // sparse lists visited so far = staging slot of the next one
   while (m) {
     const int i = __ffs((int)m) - 1;
     m &= m - 1u;
-    const uint32_t den = __shfl_sync(0xFFFFFFFFu, T.den, i);
-    if (den != OI_BM25_NONE) {
+    if ((dmask >> i) & 1u) {
+      const uint32_t den = __shfl_sync(0xFFFFFFFFu, T.den, i);
       const float4 *c0 = reinterpret_cast<const float4 *>(p.dense + (size_t)den * p.dense_stride + bbase);
       int i2 = -1;
       if (m) {
         const int cand = __ffs((int)m) - 1;
-        if (!((sm >> cand) & 1u)) i2 = cand;  // the next present term is dense too: one sweep adds both columns
+        if ((dmask >> cand) & 1u) i2 = cand;  // the next present term is dense too: one sweep adds both columns
       }
       if (i2 >= 0) {
         m &= m - 1u;
@@ -345,23 +386,60 @@ __device__ __forceinline__ void block_passes(TermRegs &T, const Bm25Params &p, f
         fresh = false;
         __syncwarp();
       }
-      const u64 base = __shfl_sync(0xFFFFFFFFu, T.base, i);
-      const uint32_t cur = __shfl_sync(0xFFFFFFFFu, T.cur, i);
-      const uint32_t end = __shfl_sync(0xFFFFFFFFu, T.end, i);
-      const uint32_t slot = (uint32_t)__popc(sm & ((1u << i) - 1u));
-      const uint4 *sp = nullptr;
+      const uint32_t mt = __shfl_sync(0xFFFFFFFFu, meta, i);
+      const uint32_t skip = mt & 1u, rem = mt >> 1;
+      const uint32_t idx = 2u * (uint32_t)lane;
+      uint4 v = make_uint4(OI_BM25_NONE, 0u, OI_BM25_NONE, 0u);
       if (slot < n_staged) {
         if (!waited) { oi_mbar_wait(mbar, phase); phase ^= 1u; waited = true; }
-        sp = stage + slot * 32u;
+        v = stage[slot * 32u + lane];
+      } else {
+        const u64 off = __shfl_sync(0xFFFFFFFFu, coff, i);
+        if (idx < rem) v = ldg_post2(p.post + off + idx);  // the array is padded: reading the pair is in bounds
       }
-      uint32_t pos_new, nxt;
-      sparse_pass(p.post, base, cur, end, bbase, bend, acc, lane, sp, &pos_new, &nxt);
-      touched += pos_new - cur;
-      if (lane == i) { T.cur = pos_new; T.nxt = nxt; }
+      ++slot;
+      if (idx + 1 >= rem) v.z = OI_BM25_NONE;             // second slot belongs to the next list
+      if (idx >= rem || idx < skip) v.x = OI_BM25_NONE;   // past the list / the leading slot below the cursor
+      const bool in0 = v.x < bend, in1 = v.z < bend;
+      if (in0) {
+        float *x = acc + (v.x - bbase);
+        const float nx = *x + __uint_as_float(v.y);  // SPEC §3: one f32 add, previous terms first
+        *x = nx;
+        mx = fmaxf(mx, nx);
+      }
+      if (in1) {
+        float *x = acc + (v.z - bbase);
+        const float nx = *x + __uint_as_float(v.w);
+        *x = nx;
+        mx = fmaxf(mx, nx);
+      }
+      const uint32_t n = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in0)) + (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in1));
+      const uint32_t sl = skip + n;  // first slot outside the block (or past the end of the list: masked to NONE above)
+      if (sl < 64u) {
+        const uint32_t nxt = __shfl_sync(0xFFFFFFFFu, (sl & 1u) ? v.z : v.x, (int)(sl >> 1));
+        touched += n;
+        if (lane == i) { T.cur += n; T.nxt = nxt; }
+      } else {  // the segment is longer than the chunk: go on with direct loads
+        const u64 base = __shfl_sync(0xFFFFFFFFu, T.base, i);
+        const uint32_t cur = __shfl_sync(0xFFFFFFFFu, T.cur, i);
+        const uint32_t end = __shfl_sync(0xFFFFFFFFu, T.end, i);
+        uint32_t pos_new, nxt;
+        sparse_pass(p.post, base, cur + n, end, bbase, bend, acc, lane, nullptr, &pos_new, &nxt, mx);
+        touched += pos_new - cur;
+        if (lane == i) { T.cur = pos_new; T.nxt = nxt; }
+      }
     }
     __syncwarp();  // the next pass may touch the same documents
   }
 }
+
+#ifdef OI_BM25_STATS
+__device__ unsigned long long g_bm25_stats[4];  // blocks scored, threshold above the dense bound, selection skipped, no threshold
+__global__ void bm25_stats_print_kernel() {
+  printf("bm25 stats: blocks %llu, thr > dense_ub %llu, skipped %llu, cold %llu\n", g_bm25_stats[0], g_bm25_stats[1], g_bm25_stats[2], g_bm25_stats[3]);
+  g_bm25_stats[0] = g_bm25_stats[1] = g_bm25_stats[2] = g_bm25_stats[3] = 0ull;
+}
+#endif
 
 // dynamic shared memory layout (per CTA, NG = warps per CTA):
 //   float  acc[NG][R]               block scores
@@ -414,6 +492,17 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
     term_setup(T0, p, q, (uint32_t)lane, nt, doc0);
     term_setup(T1, p, q, 32u + (uint32_t)lane, nt, doc0);
     if (lane == 0) { ctl->cnt = 0; ctl->thr = 0ull; ctl->aux = 0; }
+    const uint32_t dm0 = __ballot_sync(0xFFFFFFFFu, T0.den != OI_BM25_NONE);
+    const uint32_t dm1 = __ballot_sync(0xFFFFFFFFu, T1.den != OI_BM25_NONE);
+    // no document can get more than `dense_ub` from the query's dense terms: the sum of the columns' largest weights
+    // (any association; the factor covers the rounding difference to the SPEC-order sum of a real document)
+    float dense_ub = (T0.den != OI_BM25_NONE ? __ldg(p.dense_max + T0.den) : 0.0f) + (T1.den != OI_BM25_NONE ? __ldg(p.dense_max + T1.den) : 0.0f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dense_ub += __shfl_xor_sync(0xFFFFFFFFu, dense_ub, o);
+    dense_ub *= 1.0001f;
+#ifdef OI_BM25_NOSKIP
+    dense_ub = 3.0e38f;
+#endif
     __syncwarp();
 
     uint32_t blk = blk0;
@@ -430,12 +519,30 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
       const u64 gthr_now = ld_relaxed_u64(p.gthr + q);
       bool fresh = true;  // acc[] holds the previous block's scores until the first pass overwrites or clears it
       uint32_t touched = 0;
-      block_passes<RT>(T0, p, acc, stage, mbar, phase, fresh, touched, bbase, bend, lane);
-      if (nt > 32) block_passes<RT>(T1, p, acc, stage, mbar, phase, fresh, touched, bbase, bend, lane);
+      float mx = 0.0f;
+      block_passes<RT>(T0, dm0, p, acc, stage, mbar, phase, fresh, touched, mx, bbase, bend, lane);
+      if (nt > 32) block_passes<RT>(T1, dm1, p, acc, stage, mbar, phase, fresh, touched, mx, bbase, bend, lane);
       // ---- selection: positive scores that beat the running threshold -------------------------
       const u64 thr = max(ctl->thr, gthr_now);
       float tsc = thr ? oi_key_score(thr) : 0.0f;  // a survivor has score >= tsc (and > 0)
       __syncwarp();
+      // Once the threshold exceeds what the dense terms alone can give, a survivor must hold a sparse posting, and
+      // the sparse passes saw every such document's score as it grew (weights are >= 0, so a score that ends at or
+      // above the threshold was at or above it in the last pass that touched it): no lane saw one -> nothing to
+      // select, and the sweep over the block's 2048 scores -- a fifth of the kernel's instructions -- is skipped.
+#ifdef OI_BM25_STATS
+      if (lane == 0) {
+        atomicAdd(&g_bm25_stats[0], 1ull);
+        if (tsc > dense_ub) atomicAdd(&g_bm25_stats[1], 1ull);
+        if (thr == 0ull) atomicAdd(&g_bm25_stats[3], 1ull);
+      }
+      if (tsc > dense_ub && !__any_sync(0xFFFFFFFFu, mx >= tsc)) {
+        if (lane == 0) atomicAdd(&g_bm25_stats[2], 1ull);
+        continue;
+      }
+#else
+      if (tsc > dense_ub && !__any_sync(0xFFFFFFFFu, mx >= tsc)) continue;
+#endif
       if (thr == 0ull && p.cold_bound && touched + ctl->cnt > cap) {
         // cold start (no threshold yet: the first block of an item whose query has none either, i.e. every block of a
         // single-query call) and more positive scores than the buffer can take: without a bound every one of them
@@ -541,12 +648,41 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
       }
       __syncwarp();
     }
-    // ---- item done: publish the sorted list ---------------------------------------------------
+    // ---- item done: publish the sorted list, and fold it into the query's running best-k ----------
     grp_compact(cand, ctl, cap, k, g);
     if (lane == 0 && ctl->cnt == k) atomicMax(p.gthr + q, ctl->thr);
     u64 *out = p.lists + ((size_t)s * p.nq + q) * k;
-    const uint32_t cnt = ctl->cnt;
+    const uint32_t cnt = ctl->cnt;  // <= k, and 2k <= cap
     for (uint32_t i = lane; i < k; i += 32) out[i] = i < cnt ? cand[i] : 0ull;
+    // best[q][0..k) = the best k keys of the items of query q folded in so far (sorted, 0 = empty); its k-th key is
+    // published as the grid-wide threshold.  An item's own k-th best only bounds the documents of its super-range;
+    // the folded list bounds everything scored so far, so the items that start later filter with (nearly) the final
+    // threshold: the survivors of a query fall from ~k per item to ~k ln(items) in all and most blocks skip the
+    // selection sweep.  It only accelerates -- the result is still the merge of the per-item lists -- so an item
+    // that finds the list locked (queries of rare terms finish their items in bursts) or has nothing above the
+    // current threshold simply does not contribute.
+    if (cnt && cand[0] > ld_relaxed_u64(p.gthr + q)) {
+      uint32_t got = 0;
+      if (lane == 0) {
+        got = atomicCAS(p.qlock + q, 0u, 1u) == 0u;
+        if (got) __threadfence();
+      }
+      if (__shfl_sync(0xFFFFFFFFu, got, 0)) {
+        u64 *best = p.best + (size_t)q * k;
+        for (uint32_t i = lane; i < k; i += 32) cand[cnt + i] = __ldcg(best + i);
+        __syncwarp();
+        if (lane == 0) ctl->cnt = cnt + k;
+        __syncwarp();
+        grp_compact(cand, ctl, cap, k, g);
+        for (uint32_t i = lane; i < k; i += 32) __stcg(best + i, cand[i]);  // empty slots are 0 keys: they sort last
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          if (cand[k - 1]) atomicMax(p.gthr + q, cand[k - 1]);
+          atomicExch(p.qlock + q, 0u);
+        }
+      }
+    }
   }
 }
 
@@ -556,14 +692,16 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
 // query is one 32-id chunk: all list-length loads in flight at once, then ranks by counting.
 __global__ void __launch_bounds__(128) bm25_prep_queries_kernel(const uint32_t *q_terms, const uint32_t *q_offs, uint32_t nq,
                                                                const u64 *term_off, uint32_t n_terms, uint32_t *out_terms,
-                                                               uint32_t *out_nt, u64 *gthr, uint32_t *counter) {
+                                                               uint32_t *out_nt, u64 *gthr, uint32_t *counter, u64 *best,
+                                                               uint32_t k, uint32_t *qlock) {
   __shared__ uint32_t s_kept[4][OI_BM25_MAX_QTERMS];
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   uint32_t *kept = s_kept[threadIdx.x >> 5];
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
   if (q >= nq) return;  // warp-uniform
-  if (lane == 0) gthr[q] = 0ull;
+  if (lane == 0) { gthr[q] = 0ull; qlock[q] = 0u; }
+  for (uint32_t i = lane; i < k; i += 32) best[(size_t)q * k + i] = 0ull;
   const uint32_t lo = q_offs[q];
   const uint32_t n_in = q_offs[q + 1] - lo;
   uint32_t n_kept = 0;
@@ -597,34 +735,90 @@ __global__ void __launch_bounds__(128) bm25_prep_queries_kernel(const uint32_t *
   if (lane == 0) out_nt[q] = n_kept;
 }
 
+// Term of posting p = the last t with term_off[t] <= p, searched inside [lo, hi) (invariant: term_off[lo] <= p <
+// term_off[hi]).  The per-posting kernels below walk the postings in warp tiles of 256: two full searches per tile (its
+// first and last posting) bound every other search to the few terms the tile spans -- none at all in the long lists.
+__device__ __forceinline__ uint32_t bm25_term_of(const u64 *__restrict__ term_off, uint32_t lo, uint32_t hi, u64 p) {
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(term_off + mid) <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+#define OI_BM25_TILE 256u
+struct TileTerms { uint32_t lo, hi; };
+__device__ __forceinline__ TileTerms bm25_tile_terms(const u64 *__restrict__ term_off, uint32_t n_terms, u64 tile, u64 n_postings, int lane) {
+  const u64 last = min(tile + OI_BM25_TILE - 1, n_postings - 1);
+  uint32_t b = 0;
+  if (lane == 0) b = bm25_term_of(term_off, 0, n_terms, tile);
+  if (lane == 31) b = bm25_term_of(term_off, 0, n_terms, last);
+  TileTerms t;
+  t.lo = __shfl_sync(0xFFFFFFFFu, b, 0);
+  t.hi = __shfl_sync(0xFFFFFFFFu, b, 31) + 1;
+  return t;
+}
+
 // per-posting folded weight, SPEC §3 association, one IEEE op per line (file built with -fmad=false)
-__global__ void bm25_weights_kernel(const u64 *term_off, const uint32_t *doc_ids, const uint32_t *tfs,
+__global__ void __launch_bounds__(256) bm25_weights_kernel(const u64 *term_off, const uint32_t *doc_ids, const uint32_t *tfs,
                                     const uint32_t *doc_len, const float *idf, uint32_t n_terms, u64 n_postings,
                                     float k1, float b, float avgdl, float *w, uint2 *post, const int *dense_slot, float *dense,
                                     uint32_t dense_stride) {
   const float one_minus_b = 1.0f - b;
   const float k1p1 = k1 + 1.0f;
-  for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < n_postings; p += (u64)gridDim.x * blockDim.x) {
-    // term of posting p: last t with term_off[t] <= p
-    uint32_t lo = 0, hi = n_terms;  // invariant: term_off[lo] <= p < term_off[hi]
-    while (hi - lo > 1) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (__ldg(term_off + mid) <= p) lo = mid; else hi = mid;
+  const int lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 tile = warp * OI_BM25_TILE; tile < n_postings; tile += n_warps * OI_BM25_TILE) {
+    const TileTerms tt = bm25_tile_terms(term_off, n_terms, tile, n_postings, lane);
+    uint32_t lo = tt.lo;
+    for (uint32_t u = 0; u < OI_BM25_TILE / 32; ++u) {
+      const u64 p = tile + 32u * u + (uint32_t)lane;
+      if (p >= n_postings) break;
+      lo = bm25_term_of(term_off, lo, tt.hi, p);
+      const float dl = (float)doc_len[doc_ids[p]];
+      const float ratio = dl / avgdl;
+      const float bt = b * ratio;
+      const float uu = one_minus_b + bt;
+      const float norm = k1 * uu;
+      const float tf = (float)tfs[p];
+      const float num = tf * k1p1;
+      const float den = tf + norm;
+      const float qv = num / den;
+      const float wv = idf[lo] * qv;
+      w[p] = wv;
+      post[p] = make_uint2(doc_ids[p], __float_as_uint(wv));
+      const int slot = dense_slot[lo];
+      if (slot >= 0) dense[(size_t)slot * dense_stride + doc_ids[p]] = wv;
     }
-    const float dl = (float)doc_len[doc_ids[p]];
-    const float ratio = dl / avgdl;
-    const float bt = b * ratio;
-    const float u = one_minus_b + bt;
-    const float norm = k1 * u;
-    const float tf = (float)tfs[p];
-    const float num = tf * k1p1;
-    const float den = tf + norm;
-    const float qv = num / den;
-    const float wv = idf[lo] * qv;
-    w[p] = wv;
-    post[p] = make_uint2(doc_ids[p], __float_as_uint(wv));
-    const int slot = dense_slot[lo];
-    if (slot >= 0) dense[(size_t)slot * dense_stride + doc_ids[p]] = wv;
+  }
+}
+
+// largest weight of every dense column (weights are >= 0: the bit patterns order like the values)
+__global__ void __launch_bounds__(256) bm25_dense_max_kernel(const float *dense, uint32_t dense_stride, uint32_t n_docs, uint32_t *out_bits) {
+  const float *col = dense + (size_t)blockIdx.y * dense_stride;
+  float m = 0.0f;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_docs; i += gridDim.x * blockDim.x) m = fmaxf(m, col[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
+}
+
+// CSR validation on the device (oi_index_load_bm25): every doc id inside the shard, strictly ascending inside a list.
+// *err = the smallest offending posting index << 1 | kind (0 = doc id outside the shard, 1 = not ascending); ~0 = none.
+__global__ void __launch_bounds__(256) bm25_validate_kernel(const u64 *term_off, const uint32_t *doc_ids, uint32_t n_terms, u64 n_postings,
+                                                            uint32_t n_docs, u64 *err) {
+  const int lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 tile = warp * OI_BM25_TILE; tile < n_postings; tile += n_warps * OI_BM25_TILE) {
+    const TileTerms tt = bm25_tile_terms(term_off, n_terms, tile, n_postings, lane);
+    uint32_t lo = tt.lo;
+    for (uint32_t u = 0; u < OI_BM25_TILE / 32; ++u) {
+      const u64 p = tile + 32u * u + (uint32_t)lane;
+      if (p >= n_postings) break;
+      lo = bm25_term_of(term_off, lo, tt.hi, p);
+      const uint32_t d = doc_ids[p];
+      if (d >= n_docs) atomicMin(err, p << 1);
+      else if (p > term_off[lo] && d <= doc_ids[p - 1]) atomicMin(err, (p << 1) | 1ull);
+    }
   }
 }
 
@@ -733,8 +927,8 @@ void oi_bm25_free(oi_index *h) {
   OiBm25 *b = h->bm25;
   if (!b) return;
   cudaFree(b->d_term_off); cudaFree(b->d_doc_ids); cudaFree(b->d_tfs); cudaFree(b->d_doc_len); cudaFree(b->d_w);
-  cudaFree(b->d_post); cudaFree(b->d_dense); cudaFree(b->d_dense_slot);
-  cudaFree(b->d_qterms); cudaFree(b->d_qnt); cudaFree(b->d_gthr); cudaFree(b->d_counter); cudaFree(b->d_lists);
+  cudaFree(b->d_post); cudaFree(b->d_dense); cudaFree(b->d_dense_slot); cudaFree(b->d_dense_max);
+  cudaFree(b->d_qterms); cudaFree(b->d_qnt); cudaFree(b->d_gthr); cudaFree(b->d_counter); cudaFree(b->d_lists); cudaFree(b->d_best); cudaFree(b->d_qlock);
   cudaFree(b->d_in_terms); cudaFree(b->d_in_offs);
   delete b;
   h->bm25 = nullptr;
@@ -755,6 +949,8 @@ static oi_status bm25_alloc_workspace(oi_index *h, OiBm25 *b) {
   BM_CK(cudaMalloc(&b->d_counter, sizeof(uint32_t)));
   b->lists_cap = bm25_lists_cap(h);
   BM_CK(cudaMalloc(&b->d_lists, b->lists_cap * sizeof(u64)));
+  BM_CK(cudaMalloc(&b->d_best, B * (size_t)h->desc.max_k * sizeof(u64)));
+  BM_CK(cudaMalloc(&b->d_qlock, B * sizeof(uint32_t)));
   BM_CK(cudaMalloc(&b->d_in_terms, B * OI_BM25_MAX_QTERMS * sizeof(uint32_t)));
   BM_CK(cudaMalloc(&b->d_in_offs, (B + 1) * sizeof(uint32_t)));
   return OI_OK;
@@ -770,11 +966,6 @@ extern "C" oi_status oi_index_load_bm25(oi_index *h, const uint64_t *term_offset
   if (term_offsets[0] != 0) return h->fail(OI_ERR_INVALID_ARG, "term_offsets[0] must be 0");
   for (uint32_t t = 0; t < n_terms; ++t)
     if (term_offsets[t + 1] < term_offsets[t]) return h->fail(OI_ERR_INVALID_ARG, "term_offsets not monotone at term %u", t);
-  for (uint32_t t = 0; t < n_terms; ++t)
-    for (uint64_t p = term_offsets[t]; p < term_offsets[t + 1]; ++p) {
-      if (doc_ids[p] >= h->desc.n_docs) return h->fail(OI_ERR_INVALID_ARG, "posting %llu: doc id %u outside the shard", (unsigned long long)p, doc_ids[p]);
-      if (p > term_offsets[t] && doc_ids[p] <= doc_ids[p - 1]) return h->fail(OI_ERR_INVALID_ARG, "term %u: doc ids must be strictly ascending inside a list", t);
-    }
   BM_CK(cudaSetDevice(h->desc.device));
   oi_bm25_free(h);
   OiBm25 *b = new OiBm25();
@@ -793,7 +984,30 @@ extern "C" oi_status oi_index_load_bm25(oi_index *h, const uint64_t *term_offset
     BM_CK(cudaMemcpyAsync(b->d_tfs, tfs, P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   }
   if (h->desc.n_docs) BM_CK(cudaMemcpyAsync(b->d_doc_len, doc_len, h->desc.n_docs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-  BM_CK(cudaStreamSynchronize(h->stream));
+  // the postings are validated where they now are (one pass at HBM speed instead of an O(P) host loop)
+  u64 bad = ~0ull;
+  if (P) {
+    u64 *d_err = nullptr;
+    BM_CK(cudaMalloc(&d_err, sizeof(u64)));
+    cudaError_t e = cudaMemsetAsync(d_err, 0xFF, sizeof(u64), h->stream);
+    if (e == cudaSuccess) {
+      bm25_validate_kernel<<<grid_for(P / 8 + 1, 256, h->num_sms), 256, 0, h->stream>>>(b->d_term_off, b->d_doc_ids, n_terms, P, (uint32_t)h->desc.n_docs, d_err);
+      ++h->launches;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_err, sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_err);
+    BM_CK(e);
+  } else {
+    BM_CK(cudaStreamSynchronize(h->stream));
+  }
+  if (bad != ~0ull) {
+    const uint64_t pb = bad >> 1;
+    oi_bm25_free(h);
+    if (bad & 1ull) return h->fail(OI_ERR_INVALID_ARG, "posting %llu: doc ids must be strictly ascending inside a list", (unsigned long long)pb);
+    return h->fail(OI_ERR_INVALID_ARG, "posting %llu: doc id %u outside the shard", (unsigned long long)pb, doc_ids[pb]);
+  }
   return bm25_alloc_workspace(h, b);
 }
 
@@ -979,8 +1193,8 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
     b->n_dense = (uint32_t)heavy.size();
   }
   b->dense_stride = (uint32_t)(((size_t)h->desc.n_docs + OI_BM25_ACC_FLOATS - 1) / OI_BM25_ACC_FLOATS * OI_BM25_ACC_FLOATS);
-  cudaFree(b->d_post); cudaFree(b->d_dense); cudaFree(b->d_dense_slot);
-  b->d_post = nullptr; b->d_dense = nullptr; b->d_dense_slot = nullptr;
+  cudaFree(b->d_post); cudaFree(b->d_dense); cudaFree(b->d_dense_slot); cudaFree(b->d_dense_max);
+  b->d_post = nullptr; b->d_dense = nullptr; b->d_dense_slot = nullptr; b->d_dense_max = nullptr;
   const size_t dense_elems = (size_t)std::max<uint32_t>(b->n_dense, 1) * b->dense_stride;
   BM_CK(cudaMalloc(&b->d_post, ((size_t)b->n_postings + OI_BM25_POST_PAD) * sizeof(uint2)));
   BM_CK(cudaMalloc(&b->d_dense, std::max<size_t>(dense_elems, 4) * sizeof(float)));
@@ -988,6 +1202,8 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
   BM_CK(cudaMemsetAsync(b->d_post, 0xFF, ((size_t)b->n_postings + OI_BM25_POST_PAD) * sizeof(uint2), st));
   BM_CK(cudaMemsetAsync(b->d_dense, 0, std::max<size_t>(dense_elems, 4) * sizeof(float), st));
   BM_CK(cudaMemcpyAsync(b->d_dense_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  BM_CK(cudaMalloc(&b->d_dense_max, OI_BM25_MAX_DENSE * sizeof(float)));
+  BM_CK(cudaMemsetAsync(b->d_dense_max, 0, OI_BM25_MAX_DENSE * sizeof(float), st));
   float *d_idf = nullptr;
   BM_CK(cudaMalloc(&d_idf, (size_t)b->n_terms * sizeof(float)));
   cudaError_t e = cudaMemcpyAsync(d_idf, idf.data(), idf.size() * sizeof(float), cudaMemcpyHostToDevice, st);
@@ -995,6 +1211,12 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
     bm25_weights_kernel<<<grid_for(b->n_postings, 256, h->num_sms), 256, 0, st>>>(b->d_term_off, b->d_doc_ids, b->d_tfs, b->d_doc_len, d_idf,
                                                                                   b->n_terms, b->n_postings, params->k1, params->b, avgdl, b->d_w,
                                                                                   b->d_post, b->d_dense_slot, b->d_dense, b->dense_stride);
+    ++h->launches;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && b->n_dense && h->desc.n_docs) {
+    bm25_dense_max_kernel<<<dim3(64, b->n_dense), 256, 0, st>>>(b->d_dense, b->dense_stride, (uint32_t)h->desc.n_docs,
+                                                                reinterpret_cast<uint32_t *>(b->d_dense_max));
     ++h->launches;
     e = cudaGetLastError();
   }
@@ -1037,14 +1259,14 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   if (!b || !b->finalized) return h->fail(OI_ERR_STATE, "BM25 index not loaded / not finalized");
   if (nq == 0) return OI_OK;
   bm25_prep_queries_kernel<<<(nq + 3) / 4, 128, 0, st>>>(d_q_terms, d_q_offs, nq, b->d_term_off, b->n_terms,
-                                                             b->d_qterms, b->d_qnt, b->d_gthr, b->d_counter);
+                                                             b->d_qterms, b->d_qnt, b->d_gthr, b->d_counter, b->d_best, k, b->d_qlock);
   ++h->launches;
   BM_CK(cudaGetLastError());
 
   Bm25Params p;
   p.term_off = b->d_term_off; p.doc_ids = b->d_doc_ids; p.post = b->d_post;
-  p.dense = b->d_dense; p.dense_slot = b->d_dense_slot; p.dense_stride = b->dense_stride;
-  p.qterms = b->d_qterms; p.qnt = b->d_qnt; p.gthr = b->d_gthr; p.counter = b->d_counter; p.lists = b->d_lists;
+  p.dense = b->d_dense; p.dense_slot = b->d_dense_slot; p.dense_max = b->d_dense_max; p.dense_stride = b->dense_stride;
+  p.qterms = b->d_qterms; p.qnt = b->d_qnt; p.gthr = b->d_gthr; p.counter = b->d_counter; p.lists = b->d_lists; p.best = b->d_best; p.qlock = b->d_qlock;
   p.n_docs = (uint32_t)h->desc.n_docs; p.doc_base = (uint32_t)h->desc.doc_base; p.nq = nq; p.k = k;
   uint32_t cap = 256;
   while (cap < 2 * k) cap <<= 1;
@@ -1122,6 +1344,9 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   else bm25_blocked_kernel<512, 0><<<grid, ng * 32, smem, st>>>(p);
   ++h->launches;
   BM_CK(cudaGetLastError());
+#ifdef OI_BM25_STATS
+  bm25_stats_print_kernel<<<1, 1, 0, st>>>();
+#endif
   BM_CK(oi_launch_merge_shards(b->d_lists, p.S, nq, k, d_out_keys, st, &h->launches));
   return OI_OK;
 }

@@ -156,6 +156,31 @@ def test_bm25_edge_cases(oi):
         assert ids0.shape == (0, k)
 
 
+def test_load_bm25_rejects_a_malformed_csr(oi):
+    """The postings are validated on the device after the copy: doc ids inside the shard, strictly ascending per list."""
+    n, vocab = 3000, 200
+    corp = O.synth_bm25_corpus(n, vocab)
+    off = corp["term_offsets"]
+    with oi.GpuIndex(n_docs=n, dim=64, max_k=5) as ix:
+        long_t = int(np.argmax(np.diff(off)))
+        p = int(off[long_t]) + 3
+        bad = corp["doc_ids"].copy()
+        bad[p] = n + 7
+        with pytest.raises(oi.OiError) as e:
+            ix.load_bm25(off, bad, corp["tfs"], corp["doc_len"])
+        assert e.value.status == 1 and "outside the shard" in str(e.value) and str(p) in str(e.value)
+        bad = corp["doc_ids"].copy()
+        bad[p] = bad[p - 1]
+        with pytest.raises(oi.OiError) as e:
+            ix.load_bm25(off, bad, corp["tfs"], corp["doc_len"])
+        assert e.value.status == 1 and "ascending" in str(e.value)
+        # the first posting of a list may be smaller than the last posting of the previous list
+        ix.load_bm25(off, corp["doc_ids"], corp["tfs"], corp["doc_len"])
+        ix.bm25_finalize()
+        ids, _ = ix.search_bm25([[long_t]], 5)
+        assert ids[0][0] != oi.NO_DOC
+
+
 def test_bm25_before_finalize_is_a_state_error(oi):
     corp = O.synth_bm25_corpus(500, 100)
     with oi.GpuIndex(n_docs=500, dim=64, max_k=5) as ix:
