@@ -326,7 +326,7 @@ extern "C" oi_status oi_index_set_option(oi_index *h, const char *name, int64_t 
     return OI_OK;
   }
   if (!strcmp(name, "bm25_items_per_warp")) {
-    OI_REQUIRE(value >= 0 && value <= 32, "bm25_items_per_warp must be in 0..32 (0 = default)");
+    OI_REQUIRE(value >= 0 && value <= 256, "bm25_items_per_warp must be in 0..256 (0 = default)");
     h->bm25_items_per_warp = (int)value;
     return OI_OK;
   }

@@ -934,10 +934,11 @@ void oi_bm25_free(oi_index *h) {
   h->bm25 = nullptr;
 }
 
-// capacity of the per-item list workspace in KEYS: a generous schedule at k <= 128 (24 items per warp, up to 24 warps
-// per CTA) or two lists per query at max_k, whichever is larger; a call that would need more lowers its item count
+// capacity of the per-item list workspace in KEYS: up to 1024 lists per query of a full batch at max_k, at most 32 M
+// keys (256 MB), at least two lists per query; a call that would need more lowers its item count
 static size_t bm25_lists_cap(const oi_index *h) {
-  const size_t a = (size_t)24 * h->num_sms * 24 * 128, b = 2 * (size_t)h->desc.max_batch * h->desc.max_k;
+  const size_t per = (size_t)h->desc.max_batch * h->desc.max_k;
+  const size_t a = std::min<size_t>(1024 * per, (size_t)32 << 20), b = 2 * per;
   return (a > b ? a : b) + 64 * (size_t)h->desc.max_k;
 }
 
@@ -1312,14 +1313,16 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
   if (overlap == 2) grid = (uint32_t)std::max(1, h->num_sms - h->overlap_gemm_sms);
   const uint32_t groups = grid * ng;
   // super-ranges per query: enough work items (S x nq) for every warp to take ~16, so that the last items to finish
-  // (queries differ a lot in cost: zero to several dense terms) leave the SMs idle for a small part of the launch
-  // (an item also pays a fixed price -- one binary search per term to position the cursors --, so small shards take
-  // fewer, longer items: below ~32 blocks per item 8 items per warp measure 4 % faster than 16 at 6.25M documents)
+  // (queries differ a lot in cost: zero to several dense terms) leave the SMs idle for a small part of the launch,
+  // and items of at most ~32 blocks: the warps in flight then walk a narrow window of the shard (dense columns and
+  // postings are re-read from L2, not HBM) and a finished item tightens the query's threshold early.  An item pays a
+  // fixed price (one binary search per term, one fold), which is what keeps items from being smaller still
+  // (sweeps at 6.25M / 12.5M / 50M documents, batch 256, and 10M, batch 1024: docs/NOTES_r02.md).
   uint32_t ipw = h->bm25_items_per_warp > 0 ? (uint32_t)h->bm25_items_per_warp : 16;
-  if (h->bm25_items_per_warp <= 0 && (uint64_t)p.n_blocks * nq < (uint64_t)32 * ipw * groups) ipw = 8;
   uint32_t S = (ipw * groups + nq - 1) / nq;
+  if (h->bm25_items_per_warp <= 0) S = std::max(std::min(S, 256u), (p.n_blocks + 31) / 32);
   if (S < 1) S = 1;
-  if (S > 256) S = 256;  // the per-query merge is one CTA per query: a few hundred sorted lists at most
+  if (S > 1024) S = 1024;  // the per-query merge is one CTA per query: its prefix tables hold 1024 lists
   while (S > 1 && (size_t)S * nq * k > b->lists_cap) --S;
   if (S > p.n_blocks) S = p.n_blocks;
   p.J = (p.n_blocks + S - 1) / S;
@@ -1347,6 +1350,6 @@ oi_status oi_bm25_local_keys(oi_index *h, const uint32_t *d_q_terms, const uint3
 #ifdef OI_BM25_STATS
   bm25_stats_print_kernel<<<1, 1, 0, st>>>();
 #endif
-  BM_CK(oi_launch_merge_shards(b->d_lists, p.S, nq, k, d_out_keys, st, &h->launches));
+  BM_CK(oi_launch_merge_shards(b->d_lists, p.S, nq, k, d_out_keys, st, &h->launches, 0, b->d_gthr));
   return OI_OK;
 }

@@ -94,11 +94,14 @@ struct SelState {
 //      ~3 dependent loads per list) and, when they fit the buffer together — the common case, a few hundred
 //      keys — copy them in place; otherwise (heavy ties, skewed lists, G > OI_SEL_CAP) stream every key
 //      through the filter + buffer.  One CTA does this per query, so it has to take microseconds.
-__device__ void merge_sorted_lists(SelState &S, const u64 *lists, uint32_t G, size_t stride, uint32_t k, int tid, int nthreads, int bar) {
+//  `known` (0 = none) is a key the caller knows at least k keys of the lists reach (the BM25 kernel's running
+//  threshold): it replaces the sampling bound when it is the stronger one.
+__device__ void merge_sorted_lists(SelState &S, const u64 *lists, uint32_t G, size_t stride, uint32_t k, int tid, int nthreads, int bar,
+                                   u64 known = 0ull) {
   bool fits = false;
   if (tid == 0) { S.cnt = 0; S.thr = 0ull; }
   oi_bar_sync(bar, nthreads);
-  if (G <= OI_SEL_CAP / 4) {
+  if (G <= OI_SEL_CAP / 2) {  // G sample keys below, 2 G prefix words above the middle of the buffer
     const uint32_t m = max(1u, G / 2);
     const uint32_t j = (k + m - 1) / m - 1;
     const uint32_t gp = oi_next_pow2(G);
@@ -107,7 +110,7 @@ __device__ void merge_sorted_lists(SelState &S, const u64 *lists, uint32_t G, si
     oi_bitonic_desc(S.buf, gp, tid, nthreads, bar);
     const u64 T = S.buf[m - 1];
     oi_bar_sync(bar, nthreads);
-    const u64 bound = T > 0 ? T - 1 : 0;
+    const u64 bound = max(T > 0 ? T - 1 : 0ull, known > 0 ? known - 1 : 0ull);
     uint32_t *s_n = reinterpret_cast<uint32_t *>(S.buf + OI_SEL_CAP / 2);  // [G] prefix lengths, then [G] offsets
     uint32_t *s_off = s_n + G;
     for (uint32_t c = tid; c < G; c += nthreads) {
@@ -956,11 +959,12 @@ __global__ void unpack_keys_kernel(const u64 *keys, uint32_t n, uint32_t *ids, f
 
 // One CTA per query: exact top-k of `world` sorted lists (shards after the all-gather, or the per-item lists
 // of the BM25 kernel), list r of query qi at gathered + (r * nq + qi) * k.
-__global__ void __launch_bounds__(256) merge_shards_kernel(const u64 *gathered, uint32_t world, size_t rank_stride, uint32_t k, u64 *out) {
+__global__ void __launch_bounds__(256) merge_shards_kernel(const u64 *gathered, uint32_t world, size_t rank_stride, uint32_t k, u64 *out,
+                                                           const u64 *known) {
   __shared__ SelState S;
   const int tid = threadIdx.x;
   const uint32_t qi = blockIdx.x;
-  merge_sorted_lists(S, gathered + (size_t)qi * k, world, rank_stride, k, tid, 256, 0);
+  merge_sorted_lists(S, gathered + (size_t)qi * k, world, rank_stride, k, tid, 256, 0, known ? __ldcg(known + qi) : 0ull);
   for (uint32_t i = tid; i < k; i += 256) out[(size_t)qi * k + i] = i < S.cnt ? S.buf[i] : 0ull;
 }
 
@@ -1088,9 +1092,9 @@ cudaError_t oi_launch_unpack_keys(const u64 *d_keys, uint32_t n, uint32_t *d_ids
 }
 
 cudaError_t oi_launch_merge_shards(const u64 *d_gathered, uint32_t world, uint32_t nq, uint32_t k,
-                                   u64 *d_out, cudaStream_t stream, uint64_t *launches, size_t rank_stride) {
+                                   u64 *d_out, cudaStream_t stream, uint64_t *launches, size_t rank_stride, const u64 *d_known) {
   if (nq == 0) return cudaSuccess;
-  merge_shards_kernel<<<nq, 256, 0, stream>>>(d_gathered, world, rank_stride ? rank_stride : (size_t)nq * k, k, d_out);
+  merge_shards_kernel<<<nq, 256, 0, stream>>>(d_gathered, world, rank_stride ? rank_stride : (size_t)nq * k, k, d_out, d_known);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

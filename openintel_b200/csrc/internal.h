@@ -56,9 +56,11 @@ void oi_cosine_scan_tuning(int tile_rows, int stages);  // experiments: 0 = defa
 cudaError_t oi_launch_unpack_keys(const u64 *d_keys, uint32_t n, uint32_t *d_ids, float *d_scores,
                                   cudaStream_t stream, uint64_t *launches);
 // d_gathered: [world][nq][k] keys -> d_out [nq][k] best k by key.  rank_stride = distance in keys between two
-// ranks' blocks (0 = nq * k: the blocks are dense)
+// ranks' blocks (0 = nq * k: the blocks are dense); d_known (optional, [nq]): per query a key that at least k keys
+// of its lists are known to reach (0 = none) -- lets the merge copy only the list prefixes that can matter
 cudaError_t oi_launch_merge_shards(const u64 *d_gathered, uint32_t world, uint32_t nq, uint32_t k,
-                                   u64 *d_out, cudaStream_t stream, uint64_t *launches, size_t rank_stride = 0);
+                                   u64 *d_out, cudaStream_t stream, uint64_t *launches, size_t rank_stride = 0,
+                                   const u64 *d_known = nullptr);
 
 // rrf.cu --------------------------------------------------------------------------------------
 cudaError_t oi_launch_rrf(const u64 *d_cos_keys, const u64 *d_bm25_keys, uint32_t nq, uint32_t k, uint32_t rrf_k,
