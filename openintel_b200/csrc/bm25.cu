@@ -668,19 +668,40 @@ __global__ void __launch_bounds__(MAXT, 1) bm25_blocked_kernel(const Bm25Params 
         if (got) __threadfence();
       }
       if (__shfl_sync(0xFFFFFFFFu, got, 0)) {
+        // two sorted lists of distinct keys: the merged rank of a key is its index plus the number of keys of the
+        // other list above it (one binary search each; no sort, the lock is held for a microsecond)
         u64 *best = p.best + (size_t)q * k;
-        for (uint32_t i = lane; i < k; i += 32) cand[cnt + i] = __ldcg(best + i);
+        u64 *sb = cand + cap / 2;  // cnt <= k <= cap / 2: room for a copy of the running list next to the item's own
+        for (uint32_t i = lane; i < k; i += 32) sb[i] = __ldcg(best + i);
         __syncwarp();
-        if (lane == 0) ctl->cnt = cnt + k;
-        __syncwarp();
-        grp_compact(cand, ctl, cap, k, g);
-        for (uint32_t i = lane; i < k; i += 32) __stcg(best + i, cand[i]);  // empty slots are 0 keys: they sort last
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-          if (cand[k - 1]) atomicMax(p.gthr + q, cand[k - 1]);
-          atomicExch(p.qlock + q, 0u);
+        u64 kth = 0ull;  // the key that ends at rank k - 1
+        for (uint32_t i = lane; i < k; i += 32) {
+          const u64 bk = sb[i];
+          if (bk == 0ull) continue;  // empty slots stay empty unless an own key lands there
+          uint32_t lo = 0, hi = cnt;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (cand[mid] > bk) lo = mid + 1; else hi = mid;
+          }
+          const uint32_t r = i + lo;
+          if (lo && r < k) __stcg(best + r, bk);
+          if (r == k - 1) kth = bk;
         }
+        for (uint32_t i = lane; i < cnt; i += 32) {
+          const u64 ok = cand[i];
+          uint32_t lo = 0, hi = k;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sb[mid] > ok) lo = mid + 1; else hi = mid;
+          }
+          const uint32_t r = i + lo;
+          if (r < k) __stcg(best + r, ok);
+          if (r == k - 1) kth = ok;
+        }
+        __threadfence();
+        if (kth) atomicMax(p.gthr + q, kth);  // exactly one key lands at rank k - 1, if the list is full
+        __syncwarp();
+        if (lane == 0) atomicExch(p.qlock + q, 0u);
       }
     }
   }

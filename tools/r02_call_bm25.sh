@@ -1,13 +1,14 @@
 #!/bin/bash
-# BM25 after the threshold fold: parity, headline bench, ncu capture of the kernel at configs[2]
+# BM25 after the rank-merge fold: parity + timings at the bench's shard sizes
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/bm25_tests.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_bm25.py tests/test_gpu_full_size_oracle.py tests/test_gpu_store.py -x -q -m gpu > gpurun_out/bm25_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/bm25_tests.log
 tail -3 gpurun_out/bm25_tests.log
-timeout 900 python bench.py > gpurun_out/bench_n1_b.json 2> gpurun_out/bench_n1_b.err
-echo "bench rc=$?"
-tail -c 3000 gpurun_out/bench_n1_b.json
-C="python tools/bm25_probe.py --once --batch 1024"
-timeout 300 $C > gpurun_out/plain_b.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -f -k regex:bm25_blocked -s 2 -c 1 -o gpurun_out/r02b_prof_bm25 $C > gpurun_out/ncu_b.log 2>&1
-echo "ncu rc=$?"
+timeout 600 python tools/bm25_sweep.py --docs 6250000 > gpurun_out/bm25_sweep.log 2>&1
+timeout 600 python tools/bm25_sweep.py --docs 50000000 >> gpurun_out/bm25_sweep.log 2>&1
+timeout 600 python tools/bm25_sweep.py --docs 10000000 --batch 1024 >> gpurun_out/bm25_sweep.log 2>&1
+timeout 600 python tools/bm25_sweep.py --docs 1000000 --batch 1 >> gpurun_out/bm25_sweep.log 2>&1
+timeout 600 python tools/bm25_sweep.py --docs 1000000 --batch 16 >> gpurun_out/bm25_sweep.log 2>&1
+cat gpurun_out/bm25_sweep.log
+timeout 300 python tools/bm25_probe.py --docs 10000000
