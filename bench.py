@@ -569,7 +569,8 @@ def main():
             "legs": {"cosine_ms": ms_cos, "bm25_ms": ms_bm, "sum_ms": ms_cos + ms_bm, "step_ms": step_ms,
                      "step_over_max_leg": step_ms / max(ms_cos, ms_bm), "step_over_sum_of_legs": step_ms / (ms_cos + ms_bm),
                      "bm25": {"postings_touched_per_query_per_gpu": df_sum, "algorithmic_posting_gbs": df_sum * 8 * BATCH / (ms_bm * 1e-3) / 1e9,
-                              "bound": "issue / L2 (static ncu capture: profiles/r02_ncu_bm25.md)"},
+                              "bound": "latency at 31 % occupancy; static ncu capture at configs[2] (profiles/r02_ncu_bm25.md): issue 40 % of peak "
+                                       "(smsp__issue_active), L2 -> SM 53 % of peak (lts__throughput), DRAM 3 %; not measured in this run"},
                      "exchange": args.exchange if world > 1 else None,
                      "other_exchange": other_exchange,
                      "p2p_status": (lambda st: {"batches": st[0], "timed_out": st[1]})(ix.p2p_status()) if (world > 1 and args.exchange == "p2p") else None},
