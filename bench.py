@@ -558,8 +558,8 @@ def main():
                     "timing": "wall clock around blocking oi_search_hybrid calls with pinned host buffers, max over ranks, median region"},
             "gpu_launches": res["launches"],
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
-                         "traffic": _gemm_traffic(n_local), "traffic_source": "static ncu --set full capture of the same kernel at 10M x 768, batch 256 (profiles/r02_ncu_cosine_gemm.md: DRAM read + write = 1.06 x the algorithmic bytes), scaled to this shard's rows; not measured in this run",
-                         "kernel": "cosine_gemm_kernel (tcgen05; the step's dominant kernel)",
+                         "traffic": _gemm_traffic(n_local), "traffic_source": "static ncu --set full capture of the same kernel at 10M x 768, batch 256 (profiles/r02_ncu_cosine_gemm_pair.md: DRAM read + write = 1.00 x the algorithmic bytes), scaled to this shard's rows; not measured in this run",
+                         "kernel": "cosine_gemm_pair_kernel (tcgen05.mma.cta_group::2, CTA pairs; the step's dominant kernel)",
                          "peak_source": peaks["source"] + ", bf16_tflops_sustained: the kernel is timed inside a long back-to-back loop under the power cap",
                          "frac_of_burst_peak": tf / peaks["bf16_tflops"], "flops_per_launch": flops,
                          "hbm_gbs": gbs, "hbm_frac_of_measured_copy": gbs / peaks["hbm_gbs"], "bytes_per_launch": n_local * DIM * 2,

@@ -97,7 +97,10 @@ oi_status oi_index_read_embeddings(oi_index *h, void *rows, uint64_t first_doc, 
 
 /* ---- BM25 inverted index (SPEC §3) --------------------------------------------------------- */
 /* shard-local CSR: term_offsets[n_terms+1], doc_ids/tfs[term_offsets[n_terms]] (doc ids local,
- * ascending inside a list), doc_len[n_docs].  Must be followed by oi_index_bm25_finalize. */
+ * ascending inside a list), doc_len[n_docs].  Must be followed by oi_index_bm25_finalize.
+ * The offsets are checked on the host, the postings on the device after the copy (doc ids inside the
+ * shard, strictly ascending per list): a malformed CSR is OI_ERR_INVALID_ARG naming the first bad
+ * posting, and leaves the index without a BM25 part. */
 oi_status oi_index_load_bm25(oi_index *h, const uint64_t *term_offsets, const uint32_t *doc_ids,
                              const uint32_t *tfs, const uint32_t *doc_len, uint32_t n_terms);
 /* build the synthetic shard-local CSR on the device (SPEC §9); zipf_cdf[vocab] from the host */

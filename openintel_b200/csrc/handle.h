@@ -72,8 +72,8 @@ struct oi_index {
   int gemm_debug = 0;          // timing experiments only (see GemmParams::debug)
   int gemm_sample_tiles = 0;   // probe-pass tiles per CTA override (0 = default: 1/128 of the CTA's tiles); > 0 also forces the probe on small shards
   bool gemm_force_lite = false;  // experiments: always the 96 KB-ring kernel
-  int gemm_pair = 0;           // 1: an even number of query tiles runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256); measured 5 % slower
-                               // than two independent M = 128 CTAs (profiles/r02_gemm_ab.md), so it is opt-in
+  int gemm_pair = 1;           // 1: an even number of query tiles runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256): 10 % faster
+                               // than two independent M = 128 CTAs (profiles/r02_gemm_ab.md); 0 = never
   int gemm_pair_ring = 48;     // slabs (4 KB) in a pair CTA's ring at dim 768: 24 (96 KB) or 48 (192 KB)
 
   // BM25

@@ -160,29 +160,19 @@ __device__ __forceinline__ void oi_tma_load_3d_pair(void *smem_dst, const CUtens
       "l"(m), "r"(oi_smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// arrive on the mbarrier at this offset in CTA `cta` of the cluster (release at cluster scope)
+// arrive on the mbarrier at this offset in CTA `cta` of the cluster.  Default semantics (release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive: what the barrier hands over here is tensor memory, ordered by the tcgen05 fences
+// on both sides -- a `.release.cluster` arrive costs a device-wide MEMBAR per call (37 % of the pair kernel's stall
+// samples: profiles/r02_gemm_ab.md).
 __device__ __forceinline__ void oi_mbar_arrive_cluster(void *bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(oi_smem_u32(bar)),
       "r"(cta)
       : "memory");
 }
-// wait that also acquires at cluster scope (the arrivals come from the peer CTA)
-__device__ __forceinline__ void oi_mbar_wait_cluster(void *bar, uint32_t parity) {
-  uint32_t a = oi_smem_u32(bar);
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP_C:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE_C;\n\t"
-      "bra WAIT_LOOP_C;\n\t"
-      "WAIT_DONE_C:\n\t"
-      "}" ::"r"(a),
-      "r"(parity)
-      : "memory");
-}
+// wait on a barrier the peer CTA arrives on (see oi_mbar_arrive_cluster: tensor memory only, plain wait)
+__device__ __forceinline__ void oi_mbar_wait_cluster(void *bar, uint32_t parity) { oi_mbar_wait(bar, parity); }
