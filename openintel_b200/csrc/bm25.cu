@@ -1164,12 +1164,14 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
   cudaStream_t st = h->stream;
   // df: global if given, else this shard's list lengths
   std::vector<uint32_t> df(b->n_terms);
+  // one copy of the offsets (8 B per term) serves both the local df and the choice of the dense columns; the O(P)
+  // work -- weights, interleaved postings, dense columns, column maxima -- stays on the device
+  std::vector<u64> off((size_t)b->n_terms + 1);
+  BM_CK(cudaMemcpyAsync(off.data(), b->d_term_off, off.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  BM_CK(cudaStreamSynchronize(st));
   if (params->global_df) {
     std::copy(params->global_df, params->global_df + b->n_terms, df.begin());
   } else {
-    std::vector<u64> off((size_t)b->n_terms + 1);
-    BM_CK(cudaMemcpyAsync(off.data(), b->d_term_off, off.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    BM_CK(cudaStreamSynchronize(st));
     for (uint32_t t = 0; t < b->n_terms; ++t) df[t] = (uint32_t)(off[t + 1] - off[t]);
   }
   const uint64_t N = params->n_docs_global ? params->n_docs_global : h->desc.n_docs;
@@ -1200,9 +1202,6 @@ extern "C" oi_status oi_index_bm25_finalize(oi_index *h, const oi_bm25_params *p
   // costs no more instructions than walking the 8-byte postings and exposes one load latency instead of several.
   std::vector<int> slot(b->n_terms, -1);
   {
-    std::vector<u64> off((size_t)b->n_terms + 1);
-    BM_CK(cudaMemcpyAsync(off.data(), b->d_term_off, off.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    BM_CK(cudaStreamSynchronize(st));
     std::vector<std::pair<u64, uint32_t>> heavy;
     const u64 div = h->bm25_dense_div > 0 ? (u64)h->bm25_dense_div : 16;
     const u64 min_df = std::max<u64>((u64)h->desc.n_docs / div, 1024);
