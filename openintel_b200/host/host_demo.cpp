@@ -91,6 +91,11 @@ static int lexicon_bench(int argc, char **argv) {
   const auto t0 = std::chrono::steady_clock::now();
   for (int r = 0; r < reps; ++r) an.run_packed(reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), n, pol.data(), spec.data(), nullptr);
   const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+  // the same call with the fused social summary (a sequential f64 sum on the device: the reference's order)
+  const auto t1 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; ++r) an.run_packed(reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), n, pol.data(), spec.data(), &sum);
+  const double s_sum = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count() / reps;
+  std::printf("lexicon-bench posts %zu with_summary_ms_per_call %.3f summary_extra_ms %.3f\n", n, s_sum * 1e3, (s_sum - s) * 1e3);
   std::printf("lexicon-bench posts %zu bytes %zu ms_per_call %.3f posts_per_s %.0f text_GBps %.3f bullish %llu bearish %llu neutral %llu net %.6f\n", n,
               blob.size(), s * 1e3, n / s, blob.size() / s / 1e9, (unsigned long long)sum.bullish, (unsigned long long)sum.bearish,
               (unsigned long long)sum.neutral, sum.net_sentiment);

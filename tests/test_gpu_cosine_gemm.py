@@ -59,6 +59,32 @@ def test_gemm_topk_parity(oi, n, dim, k, nq):
         assert np.max(np.abs(sc[j] - sc_s[j])) < 2e-5
 
 
+@pytest.mark.parametrize("n,dim,nq,k", [(4097, 768, 130, 8), (300, 128, 256, 8), (3000, 384, 200, 8), (90000, 768, 256, 100),
+                                        (20000, 64, 1024, 10)])
+def test_cta_pairs_equal_single_ctas(oi, n, dim, nq, k):
+    """An even number of query tiles runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256: the default); the raw
+    accumulators and the top-k lists must be the single-CTA kernel's bit for bit, and match the oracle."""
+    rows = O.synth_rows_bf16(n, dim)
+    qs = O.synth_rows_f32(nq, dim, stream=1)
+    with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=nq) as ix:
+        ix.load_embeddings(rows)
+        raw, lists = {}, {}
+        for pair in (1, 0):
+            ix.set_option("cosine_gemm_pair", pair)
+            if n <= 5000:
+                raw[pair] = ix.debug_cosine_gemm_scores(qs)
+            lists[pair] = ix.search_cosine(qs, k)
+    if raw:
+        assert np.array_equal(raw[0].view(np.uint32), raw[1].view(np.uint32))
+        for j in (0, nq // 2, nq - 1):
+            assert np.max(np.abs(raw[1][j] - _oracle_scores(rows, qs[j]))) < 2e-5
+    assert np.array_equal(lists[0][0], lists[1][0]) and np.array_equal(lists[0][1].view(np.uint32), lists[1][1].view(np.uint32))
+    for j in (0, nq - 1):
+        allsc = _oracle_scores(rows, qs[j])
+        wi, ws, _ = O.topk_f64(allsc, k)
+        assert_ranked_close(lists[1][0][j], lists[1][1][j], wi, ws, allsc, BF16_TOL)
+
+
 @pytest.mark.parametrize("cap,spt", [(128, 1), (256, 2), (0, 1)])
 def test_two_pass_flow_and_list_compaction(oi, cap, spt):
     """small candidate lists + a one-tile sample force the main pass and the in-kernel compaction"""
