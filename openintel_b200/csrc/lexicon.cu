@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) lexicon_kernel(const uint8_t *texts, cons
   for (unsigned long long post = warp; post < n_posts; post += n_warps) {
     const uint8_t *t = texts + offsets[post];
     const long long len = (long long)(offsets[post + 1] - offsets[post]);
+    bool ascii = false;
     if (len <= kStageBytes) {
       // the 16-byte words that cover the post, loaded aligned (the allocation is padded to whole words); the post's
       // first byte sits at `sh` inside the staged copy
@@ -110,12 +111,69 @@ __global__ void __launch_bounds__(256) lexicon_kernel(const uint8_t *texts, cons
       const int sh = (int)(reinterpret_cast<uintptr_t>(t) - a0);
       const int n_words = (int)((sh + len + 15) >> 4);
       __syncwarp();  // the previous post's readers are done with the staging area
-      for (int w = lane; w < n_words; w += 32)
-        reinterpret_cast<uint4 *>(stage)[w] = __ldg(reinterpret_cast<const uint4 *>(a0) + w);
+      uint32_t hb = 0;
+      for (int w = lane; w < n_words; w += 32) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a0) + w);
+        reinterpret_cast<uint4 *>(stage)[w] = v;
+        hb |= v.x | v.y | v.z | v.w;
+      }
       __syncwarp();
       t = stage + sh;
+      // no byte >= 0x80 in the covering words (a neighbour's bytes in the first / last word only make this conservative)
+      ascii = !__any_sync(0xFFFFFFFFu, (hb & 0x80808080u) != 0u);
     }
     uint32_t bull = 0, bear = 0, spec = 0;
+    if (ascii) {
+      // ASCII fast path (the usual post): 32 bytes per step, one ballot finds the token starts, and every start lane
+      // reads its token as 16 bytes + 1 from shared memory and classifies / lowercases them four at a time (SWAR) --
+      // no per-byte loop.  Same tokens, same packing as the general path below.
+      uint32_t carry = 0;  // was the last byte of the previous step a token byte
+      for (long long c0 = 0; c0 < len; c0 += 32) {
+        const long long i = c0 + lane;
+        const uint32_t b = i < len ? (uint32_t)t[i] : 0x20u;
+        const bool tok = ((b | 0x20u) - 'a') < 26u || (b - '0') < 10u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, tok);
+        const uint32_t starts = m & ~((m << 1) | carry);
+        carry = m >> 31;
+        if (!((starts >> lane) & 1u)) continue;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(t + i);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        const uint32_t sh8 = (uint32_t)(addr & 3u) * 8u;
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+        uint32_t x[4] = {__funnelshift_r(w0, w1, sh8), __funnelshift_r(w1, w2, sh8), __funnelshift_r(w2, w3, sh8),
+                         __funnelshift_r(w3, w4, sh8)};
+        const uint32_t b16 = (w4 >> sh8) & 0xFFu;
+        uint32_t n = 0;
+        bool run = true;  // still inside the token's leading run
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          // bytes are < 0x80: x + (0x80 - lo) sets bit 7 iff x >= lo, no carry into the next byte
+          const uint32_t v = x[u];
+          const uint32_t up = (v + 0x3F3F3F3Fu) & ~(v + 0x25252525u);  // 'A' .. 'Z'
+          const uint32_t lw = (v + 0x1F1F1F1Fu) & ~(v + 0x05050505u);  // 'a' .. 'z'
+          const uint32_t dg = (v + 0x50505050u) & ~(v + 0x46464646u);  // '0' .. '9'
+          const uint32_t tm = (up | lw | dg) & 0x80808080u;
+          x[u] = v | ((up & 0x80808080u) >> 2);                         // lower the capitals
+          const uint32_t nt = ~tm & 0x80808080u;
+          const uint32_t lead = nt ? (uint32_t)(__ffs((int)nt) - 1) >> 3 : 4u;
+          if (run) n += lead;
+          run = run && lead == 4u;
+        }
+        const bool more = run && (((b16 | 0x20u) - 'a') < 26u || (b16 - '0') < 10u);  // a 17th token byte
+        const long long left = len - i;
+        if (more && left > 16) continue;  // longer than 16 bytes: cannot match a list word
+        if ((long long)n > left) n = (uint32_t)left;
+        unsigned long long lo = (unsigned long long)x[0] | ((unsigned long long)x[1] << 32);
+        unsigned long long hi = (unsigned long long)x[2] | ((unsigned long long)x[3] << 32);
+        if (n < 8) { lo &= (1ull << (8 * n)) - 1ull; hi = 0ull; }
+        else if (n < 16) hi &= (1ull << (8 * (n - 8))) - 1ull;
+        const LexSlot e = s_tab[lex_hash(lo, hi)];
+        const uint32_t f = (e.lo == lo && e.hi == hi) ? e.flags : 0u;
+        bull += f & 1u;
+        bear += (f >> 1) & 1u;
+        spec |= (f >> 2) & 1u;
+      }
+    } else
     for (long long i = lane; i < len; i += 32) {
       const int c = classify(t, i, len);
       if (c == CLS_SEP || c == CLS_SKIP) continue;

@@ -206,3 +206,40 @@ def test_dev_calls_on_two_streams_are_ordered(oi):
         for i in range(2):
             assert np.array_equal(outs[i][0].cpu().numpy().view(np.uint32), want[i][0])
             assert np.array_equal(outs[i][1].cpu().numpy(), want[i][1])
+
+
+def test_dev_hybrid_call_is_graph_capturable(oi):
+    """The `_dev` entry points enqueue only (no allocation, no synchronisation, no event bookkeeping while the stream
+    is capturing): a hybrid call captured in a CUDA graph replays to the same lists as the plain call."""
+    import torch
+    n, dim, vocab, k, nq = 150_000, 256, 20_000, 50, 130
+    cdf = O.zipf_cdf(vocab)
+    q = O.synth_rows_f32(nq, dim, stream=1)
+    qt = O.synth_query_terms(nq, 8, cdf)
+    with oi.GpuIndex(n_docs=n, dim=dim, dtype=oi.DTYPE_BF16, max_k=k, max_batch=nq) as ix:
+        ix.synth_embeddings(O.SEED)
+        ix.synth_bm25(O.SEED, vocab, cdf)
+        ix.bm25_finalize()
+        w_ids, w_rrf, w_rc, w_rb = ix.search_hybrid(q, qt, k)
+        d_q = torch.from_numpy(q).cuda()
+        d_t = torch.from_numpy(qt.astype(np.int32).reshape(-1)).cuda()
+        d_o = torch.arange(0, nq * 8 + 1, 8, dtype=torch.int32, device="cuda")
+        o = [torch.zeros(nq, k, dtype=torch.int32, device="cuda") for _ in range(3)]
+        rrf = torch.zeros(nq, k, dtype=torch.float32, device="cuda")
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            ix.search_hybrid_dev(d_q, d_t, d_o, nq, k, 60, o[0], rrf, o[1], o[2], s.cuda_stream)  # warm-up: one-time attributes
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                ix.search_hybrid_dev(d_q, d_t, d_o, nq, k, 60, o[0], rrf, o[1], o[2], s.cuda_stream)
+            for t in o:
+                t.zero_()
+            rrf.zero_()
+            for _ in range(3):
+                g.replay()
+            s.synchronize()
+        assert np.array_equal(o[0].cpu().numpy().view(np.uint32), w_ids)
+        assert np.array_equal(rrf.cpu().numpy().view(np.uint32), w_rrf.view(np.uint32))
+        assert np.array_equal(o[1].cpu().numpy().view(np.uint32), w_rc) and np.array_equal(o[2].cpu().numpy().view(np.uint32), w_rb)
+        del g
