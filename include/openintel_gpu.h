@@ -189,12 +189,14 @@ uint64_t oi_index_launch_count(const oi_index *h);
 /* named integer knobs: "cosine_variant" (0 = ldg, 1 = bulk-copy pipeline), "cosine_gemm_min_batch"
  * (bf16 batches of at least this many queries take the tcgen05 tensor-core path; 0 = never),
  * "cosine_gemm_cap" (tests: force list compaction), "cosine_gemm_sample_tiles" (probe-pass tiles per CTA; > 0 also forces
- * the probe pass on small shards);
+ * the probe pass on small shards), "cosine_gemm_pair" (1 = default: an even number of 128-query tiles runs as CTA pairs,
+ * tcgen05.mma.cta_group::2 with M = 256; 0 = single CTAs only; same lists bit for bit), "cosine_gemm_pair_ring" (24 | 48);
  * "cosine_multi_query" (2 = default: a call with several queries reads the matrix once per group of 4 queries when a
  * row is at most 1536 bytes, on the bulk-copy pipeline for f32 rows; 1 = same with direct loads; 0 = every query
  * scans the matrix on its own);
  * BM25 schedule: "bm25_warps" (warps per CTA), "bm25_block_docs" (documents per block, power of two >= 1024),
- * "bm25_stage_slots" (TMA-staged 64-posting chunks per warp), "bm25_items_per_warp", "bm25_dense_div" (before
+ * "bm25_stage_slots" (TMA-staged 64-posting chunks per warp), "bm25_items_per_warp" (0 = default: 16 per warp and at
+ * most 32 blocks per item), "bm25_dense_div" (before
  * finalize: a term in >= n_docs / div documents gets a dense weight column), "bm25_no_cold_bound" (tests);
  * every setting returns the same lists bit for bit.
  * Hybrid call: "hybrid_overlap" (0 = default: the two legs back to back; 1 = BM25 on a second stream next to the
