@@ -1,13 +1,15 @@
 #!/bin/bash
-# BM25: extra staging slots in the idle half of the candidate buffer -- parity + A/B on the same box
+# BM25: mid-item folds -- parity + A/B on the same box + skip counters
 set -x
 cd $GRAFT_REPO_ROOT
 timeout 900 python -m pytest tests/test_gpu_bm25.py tests/test_gpu_full_size_oracle.py tests/test_gpu_store.py -x -q -m gpu > gpurun_out/bm25_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/bm25_tests.log
 tail -3 gpurun_out/bm25_tests.log
+OI_GPU_LIB=$GRAFT_REPO_ROOT/tools/probes/stats/libopenintel_gpu.so timeout 300 python tools/bm25_probe.py --once --batch 256 --docs 6250000 > gpurun_out/bm25_stats.log 2>&1
+grep "bm25 stats" gpurun_out/bm25_stats.log | tail -2
 rm -f gpurun_out/bm25_sweep.log
 for rep in 1 2; do
-for v in noxslot intree; do
+for v in base intree; do
   if [ $v = intree ]; then unset OI_GPU_LIB; else export OI_GPU_LIB=$GRAFT_REPO_ROOT/tools/probes/$v/libopenintel_gpu.so; fi
   echo "== $v" >> gpurun_out/bm25_sweep.log
   timeout 600 python tools/bm25_sweep.py --docs 6250000 >> gpurun_out/bm25_sweep.log 2>&1
