@@ -433,6 +433,9 @@ __device__ __forceinline__ void block_passes(TermRegs &T, uint32_t dmask, const 
   }
 }
 
+// Compile-time instrumentation (not in the shipped build): -DOI_BM25_STATS counts, per launch, the (query, block) pairs
+// scored, those whose threshold exceeds the dense bound, those that skip the selection sweep and those scored without
+// any threshold, and prints them after the launch (profiles/r02_ncu_bm25.md); -DOI_BM25_NOSKIP disables the skip (A/B).
 #ifdef OI_BM25_STATS
 __device__ unsigned long long g_bm25_stats[4];  // blocks scored, threshold above the dense bound, selection skipped, no threshold
 __global__ void bm25_stats_print_kernel() {
