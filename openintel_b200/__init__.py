@@ -7,6 +7,7 @@ fallback: importing works anywhere, but every compute call needs the CUDA librar
 """
 from .capi import (GpuIndex, OiError, NO_DOC, DTYPE_F32, DTYPE_BF16, lib_path, load_library,  # noqa: F401
                    lexicon_analyze, version, GpuLexicon, pack_texts)
+from . import fusion  # noqa: F401  (host-side crowding / alignment / confidence on the GPU analyzer's summary)
 
 __all__ = ["GpuIndex", "OiError", "NO_DOC", "DTYPE_F32", "DTYPE_BF16", "lib_path", "load_library",
-           "lexicon_analyze", "version", "GpuLexicon", "pack_texts"]
+           "lexicon_analyze", "version", "GpuLexicon", "pack_texts", "fusion"]

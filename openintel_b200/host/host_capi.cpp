@@ -106,4 +106,25 @@ uint32_t oih_builder_post_id(void *b, uint32_t doc, uint8_t *out, uint32_t cap) 
   return (uint32_t)s.size();
 }
 
+// fusion signals (openintel_host.hpp: crowding / alignment / confidence) with the default EngineConfig
+double oih_crowding(uint64_t total, double speculation_index, int has_market, int has_rvol, double rvol, int has_iv, double iv_rank) {
+  using namespace openintel;
+  SocialSummary s;
+  s.total = total;
+  s.speculation_index = speculation_index;
+  MarketSummary m;
+  m.has_rvol = has_rvol != 0; m.rvol = rvol; m.has_iv_rank = has_iv != 0; m.iv_rank = iv_rank;
+  return crowding(s, has_market ? &m : nullptr);
+}
+int oih_alignment(uint64_t total, double net_sentiment, int has_market, double pct_change) {
+  using namespace openintel;
+  SocialSummary s;
+  s.total = total;
+  s.net_sentiment = net_sentiment;
+  MarketSummary m;
+  m.pct_change = pct_change;
+  return (int)alignment(s, has_market ? &m : nullptr);
+}
+int oih_confidence(uint64_t n, uint64_t low, uint64_t high) { return (int)openintel::confidence(n, low, high); }
+
 }  // extern "C"

@@ -11,6 +11,7 @@
 // Header-only; compute happens in libopenintel_gpu.so.  No CPU scoring path exists here either.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -266,6 +267,55 @@ struct SocialSummary {
   double net_sentiment = 0.0, speculation_index = 0.0;
   double bull_bear_ratio = -1.0;  // -1: no bearish post (the reference's Option::None)
 };
+
+// ---- fusion signals on top of the summary: what SpeculationEngine::aggregate derives next (O(1) scalar arithmetic on
+// the summary and a market snapshot; src/domain/engine/speculation_engine.rs:43-66).  Host code by design.
+struct EngineConfig {  // src/domain/engine/config.rs:2-33, same names and defaults
+  double bull_bear_threshold = 0.2, net_sentiment_threshold = 0.05, price_move_threshold = 1.0;
+  double crowding_weight_spec = 0.5, crowding_weight_rvol = 0.3, crowding_weight_iv = 0.2, rvol_cap = 3.0;
+  uint64_t min_sample = 10, confidence_low = 10, confidence_high = 50;
+};
+struct MarketSummary {  // the fields the fusion reads (speculation_engine.rs:127-148)
+  double pct_change = 0.0;
+  bool has_rvol = false;
+  double rvol = 0.0;
+  bool has_iv_rank = false;
+  double iv_rank = 0.0;
+  // a zero previous close gives pct_change 0, a zero average volume no rvol
+  static MarketSummary from_snapshot(double last_price, double previous_close, uint64_t volume, uint64_t avg_volume) {
+    MarketSummary m;
+    m.pct_change = previous_close == 0.0 ? 0.0 : (last_price - previous_close) / previous_close * 100.0;
+    m.has_rvol = avg_volume != 0;
+    if (m.has_rvol) m.rvol = (double)volume / (double)avg_volume;
+    return m;
+  }
+};
+enum class Alignment { ConfirmingBullish = 0, ConfirmingBearish = 1, Diverging = 2, Quiet = 3 };
+enum class Confidence { Low = 0, Medium = 1, High = 2 };
+
+inline double clamp01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }
+// weighted blend of the components that are present, renormalised over their weights (speculation_engine.rs:151-176)
+inline double crowding(const SocialSummary &s, const MarketSummary *m, const EngineConfig &cfg = EngineConfig()) {
+  double weighted = 0.0, weight_sum = 0.0;
+  if (s.total > 0) { weighted += cfg.crowding_weight_spec * s.speculation_index; weight_sum += cfg.crowding_weight_spec; }
+  if (m && m->has_rvol) { weighted += cfg.crowding_weight_rvol * clamp01(m->rvol / cfg.rvol_cap); weight_sum += cfg.crowding_weight_rvol; }
+  if (m && m->has_iv_rank) { weighted += cfg.crowding_weight_iv * clamp01(m->iv_rank); weight_sum += cfg.crowding_weight_iv; }
+  return weight_sum == 0.0 ? 0.0 : clamp01(weighted / weight_sum);
+}
+// does the crowd agree with the tape (speculation_engine.rs:178-208)
+inline Alignment alignment(const SocialSummary &s, const MarketSummary *m, const EngineConfig &cfg = EngineConfig()) {
+  if (!m || s.total < cfg.min_sample) return Alignment::Quiet;
+  const double a = s.net_sentiment, p = m->pct_change;
+  if (!(std::fabs(a) >= cfg.net_sentiment_threshold) || !(std::fabs(p) >= cfg.price_move_threshold)) return Alignment::Quiet;
+  if (a > 0.0 && p > 0.0) return Alignment::ConfirmingBullish;
+  if (!(a > 0.0) && !(p > 0.0)) return Alignment::ConfirmingBearish;
+  return Alignment::Diverging;
+}
+// sample-size bucket; reversed thresholds are normalised first (src/domain/values/speculation.rs:29-42)
+inline Confidence confidence(uint64_t n, uint64_t low, uint64_t high) {
+  const uint64_t lo = std::min(low, high), hi = std::max(low, high);
+  return n < lo ? Confidence::Low : (n < hi ? Confidence::Medium : Confidence::High);
+}
 
 // Replaces LexiconAnalyzer::analyze (src/adapters/analyzer/lexicon.rs:82-87) with the batched GPU scorer.  Owns an
 // oi_lexicon handle: the stream and the device buffers are created once and reused by every call.
