@@ -150,3 +150,43 @@ def test_store_bf16_index(oi, tmp_path):
     assert_ranked_close(cos_ids[0], cos_sc[0], wi, ws, allsc, 2e-3)
     assert len(got) == k and len({h["doc_id"] for h in got}) == k
     assert {h["doc_id"] for h in got if h["rank_cosine"]} <= set(int(i) for i in cos_ids[0])
+
+
+def test_search_posts_cli(oi, tmp_path):
+    """`python -m openintel_b200.search`: the running twin of the Rust `openintel search` subcommand / `search_posts`
+    MCP tool (rust/openintel-gpu/src/{cli_search,mcp_search}.rs): same request, same report, both renderings."""
+    import json
+    import subprocess
+    import sys
+    from openintel_b200 import search, store
+    n, vocab, dim, k = 2000, 800, 64, 7
+    posts, _ = O.synth_posts(n, vocab, O.SEED)
+    emb = O.synth_rows_f32(n, dim)
+    db = str(tmp_path / "posts.db")
+    conn = store.open_store(db, dim=dim)
+    store.insert_posts(conn, posts, emb)
+    query = " ".join(posts[11]["text"].split()[:5])
+    qv = (O.synth_rows_f32(1, dim, stream=1)[0] * np.float32(2.0)).astype("<f4")
+    qfile = tmp_path / "q.f32"
+    qfile.write_bytes(qv.tobytes())
+    with store.StoreIndex(conn, max_k=k, max_batch=1) as sx:
+        want = sx.search([query], qv[None, :], k)[0]
+        rep = search.search_posts(sx, query, qv, k)
+        assert [h["post_id"] for h in rep["hits"]] == [h["id"] for h in want] and rep["notes"] == []
+        only_vec = search.search_posts(sx, "zzzunknownzzz", qv, k)
+        assert only_vec["notes"] and all(h["rank_bm25"] is None for h in only_vec["hits"])
+        with pytest.raises(ValueError):
+            search.search_posts(sx, query, qv[:-1], k)
+        with pytest.raises(ValueError):
+            search.search_posts(sx, query, np.zeros(dim, np.float32), k)
+    conn.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "openintel_b200.search", query, "--store", db, "--embedding", str(qfile), "--k", str(k)]
+    out = subprocess.run(cmd + ["--format", "json"], cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads(out.stdout)
+    assert [h["post_id"] for h in got["hits"]] == [h["id"] for h in want]
+    assert [h.get("rank_cosine") for h in got["hits"]] == [h["rank_cosine"] or None for h in want]
+    assert abs(got["hits"][0]["rrf"] - want[0]["rrf"]) < 1e-7 and got["disclaimer"]
+    table = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=300)
+    assert table.returncode == 0 and table.stdout.splitlines()[0].startswith("rank") and len(table.stdout.splitlines()) == 1 + len(want)
