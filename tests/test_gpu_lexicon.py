@@ -109,3 +109,58 @@ def test_handle_api_and_fused_social_summary(oi, G):
             _, _, _, _, summ = lx.analyze(posts, summary=True)
         assert summ["total"] == 10 and (summ["bullish"], summ["bearish"], summ["neutral"]) == (7, 2, 1)
         assert summ["net_sentiment"] == 0.5 and summ["speculation_index"] == 0.3 and summ["bull_bear_ratio"] == 3.5
+
+
+def test_analyze_flow_over_a_post_store_matches_the_reference_fixture(tmp_path):
+    """The reference's `analyze` use case with the GPU PostAnalyzer injected (openintel_b200/analyze.py): the ten
+    fixture posts of the reference's mock sources + its mock market snapshot must give the report the reference's own
+    flow test asserts (tests/analyze_flow.rs:128-131: 10 mentions, ConfirmingBullish) and the values derived from its
+    fixtures (tests/golden/reference_lexicon_goldens.json)."""
+    import json
+    import subprocess
+    import sys
+    import oracle as O
+    from openintel_b200 import analyze, capi, fusion, store
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_lexicon_goldens.json")))
+    fx = G["fixture_posts"]
+    posts = [dict(id=p["id"], source=p["source"], author=p["author"], text=p["text"], created_at=1700000000 + i, engagement=p["engagement"])
+             for i, p in enumerate(fx["posts"])]
+    db = str(tmp_path / "fixture.db")
+    conn = store.open_store(db, dim=4)
+    store.insert_posts(conn, posts, np.ones((len(posts), 4), np.float32))
+    m = fx["mock_market"]
+    mk = fusion.MarketSummary.from_snapshot(m["last_price"], m["previous_close"], m["volume"], m["avg_volume"], m["iv_rank"])
+    ids, sources, texts = analyze.select_posts(conn)
+    assert ids == [p["id"] for p in fx["posts"]]
+    with capi.GpuLexicon() as lx:
+        rep, pol, spec = analyze.analyze_posts(lx, sources, texts, mk)
+        d = fx["summary"]["derived"]
+        assert list(pol) == [p["polarity"] for p in fx["posts"]] and list(spec) == [p["speculative"] for p in fx["posts"]]
+        s = rep["social"]
+        assert s["total_mentions"] == fx["summary"]["asserted"]["total_mentions"] == 10
+        assert (s["bullish"], s["bearish"], s["neutral"]) == (d["bullish"], d["bearish"], d["neutral"])
+        assert s["net_sentiment"] == d["net_sentiment"] and s["speculation_index"] == d["speculation_index"]
+        assert s["bull_bear_ratio"] == d["bull_bear_ratio"] and dict(s["mentions_by_source"]) == {"bluesky": 6, "reddit": 4}
+        assert rep["fusion"]["alignment"] == fx["summary"]["asserted"]["alignment"] == "ConfirmingBullish"
+        assert abs(rep["fusion"]["crowding"] - m["derived"]["crowding"]) < 1e-12 and rep["social_confidence"] == "Medium"
+        assert rep["fusion"]["crowding"] == O.crowding(10, d["speculation_index"], rvol=mk.rvol, iv=mk.iv_rank)
+        # social-only run: Quiet + the reference's note; one source only; a mention filter; nothing at all
+        solo, _, _ = analyze.analyze_posts(lx, sources, texts, None)
+        assert solo["fusion"]["alignment"] == "Quiet" and solo["fusion"]["notes"] == ["social-only, no price reference"] and solo["market"] is None
+        _, src_r, txt_r = analyze.select_posts(conn, source="reddit")
+        assert len(txt_r) == 4 and set(src_r) == {"reddit"}
+        _, _, txt_m = analyze.select_posts(conn, mention="$aapl")
+        assert 0 < len(txt_m) <= 10 and all("aapl" in t.lower() for t in txt_m)
+        with pytest.raises(analyze.NoData):
+            analyze.analyze_posts(lx, [], [], None)
+        empty, _, _ = analyze.analyze_posts(lx, [], [], mk)
+        assert empty["social"]["total_mentions"] == 0 and empty["fusion"]["alignment"] == "Quiet" and empty["social_confidence"] == "Low"
+    conn.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "openintel_b200.analyze", "--store", db, "--market",
+                          "%r,%r,%d,%d,%r" % (m["last_price"], m["previous_close"], m["volume"], m["avg_volume"], m["iv_rank"])],
+                         cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    cli = json.loads(out.stdout)
+    assert cli["fusion"]["alignment"] == "ConfirmingBullish" and cli["social"]["total_mentions"] == 10
+    assert abs(cli["fusion"]["crowding"] - m["derived"]["crowding"]) < 1e-12 and abs(cli["market"]["pct_change"] - m["derived"]["pct_change"]) < 1e-12
