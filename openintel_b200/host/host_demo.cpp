@@ -4,6 +4,8 @@
 // then one line per post "signal i polarity speculative" from the GPU PostAnalyzer.
 //   host_demo --store <posts.db> <queries.txt> <query_embeddings.f32> <k>
 // lifts the index out of a SQLite post store (openintel_store.hpp) and prints "hit q rank doc_id rrf rc rb post_id".
+//   host_demo --analyze <posts.db> [last_price previous_close volume avg_volume [iv_rank]]
+// the reference's analyze use case over a store with the GPU PostAnalyzer injected (see analyze_mode).
 //   host_demo --lexicon-bench <n_posts> [reps]
 // GPU PostAnalyzer throughput without any Python in the loop: n_posts synthetic posts are packed once in C++, then
 // `reps` calls of the handle API are timed (host buffers in, host buffers out); prints posts/s and text GB/s.
@@ -64,6 +66,42 @@ static int store_mode(int argc, char **argv) {
   return 0;
 }
 
+// host_demo --analyze <posts.db> [last_price previous_close volume avg_volume [iv_rank]]
+// The reference's `analyze` use case (src/application/analyze.rs:16-73) over the posts of a store, with the GPU
+// PostAnalyzer injected through the `PostAnalyzer` port: posts -> one device call (signals + social summary) -> fusion
+// signals on the host -> one line "report total bullish bearish neutral net spec_index crowding alignment confidence".
+static int analyze_mode(int argc, char **argv) {
+  if (argc != 3 && argc != 7 && argc != 8) {
+    std::fprintf(stderr, "usage: host_demo --analyze posts.db [last_price previous_close volume avg_volume [iv_rank]]\n");
+    return 2;
+  }
+  const SqlitePostStore store(argv[2]);
+  std::vector<SocialPost> posts;
+  store.for_each_post([&](const SocialPost &p) { posts.push_back(p); });
+  MarketSummary market;
+  const bool has_market = argc >= 7;
+  if (has_market) {
+    market = MarketSummary::from_snapshot(std::stod(argv[3]), std::stod(argv[4]), std::stoull(argv[5]), std::stoull(argv[6]));
+    if (argc == 8) { market.has_iv_rank = true; market.iv_rank = std::stod(argv[7]); }
+  }
+  if (posts.empty() && !has_market) throw DomainError::source_failure("analyze", "no data");  // DomainError::NoData
+  const EngineConfig cfg;
+  const GpuLexiconAnalyzer gpu(0);
+  const PostAnalyzer &analyzer = gpu;  // the use case sees the port only (src/application/analyze.rs:62-63 de-hard-wired)
+  (void)analyzer;
+  SocialSummary sum;
+  std::vector<PostSignal> signals;
+  if (!posts.empty()) signals = gpu.analyze(posts, &sum, cfg.bull_bear_threshold);
+  if (signals.size() != posts.size()) throw DomainError::source_failure("analyze", "analyzer mismatch");
+  static const char *kAlign[] = {"ConfirmingBullish", "ConfirmingBearish", "Diverging", "Quiet"};
+  static const char *kConf[] = {"Low", "Medium", "High"};
+  std::printf("report %llu %llu %llu %llu %.17g %.17g %.17g %s %s\n", (unsigned long long)sum.total, (unsigned long long)sum.bullish,
+              (unsigned long long)sum.bearish, (unsigned long long)sum.neutral, sum.net_sentiment, sum.speculation_index,
+              crowding(sum, has_market ? &market : nullptr, cfg), kAlign[(int)alignment(sum, has_market ? &market : nullptr, cfg)],
+              kConf[(int)confidence(sum.total, cfg.confidence_low, cfg.confidence_high)]);
+  return 0;
+}
+
 static int lexicon_bench(int argc, char **argv) {
   if (argc < 3) { std::fprintf(stderr, "usage: host_demo --lexicon-bench n_posts [reps]\n"); return 2; }
   const size_t n = std::stoul(argv[2]);
@@ -106,6 +144,17 @@ int main(int argc, char **argv) {
   if (argc >= 2 && std::string(argv[1]) == "--lexicon-bench") {
     try {
       return lexicon_bench(argc, argv);
+    } catch (const std::exception &e) {
+      std::fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
+  if (argc >= 2 && std::string(argv[1]) == "--analyze") {
+    try {
+      return analyze_mode(argc, argv);
+    } catch (const DomainError &e) {
+      std::fprintf(stderr, "DomainError(%d): %s\n", (int)e.kind, e.what());
+      return 1;
     } catch (const std::exception &e) {
       std::fprintf(stderr, "error: %s\n", e.what());
       return 1;

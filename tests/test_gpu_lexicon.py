@@ -164,3 +164,15 @@ def test_analyze_flow_over_a_post_store_matches_the_reference_fixture(tmp_path):
     cli = json.loads(out.stdout)
     assert cli["fusion"]["alignment"] == "ConfirmingBullish" and cli["social"]["total_mentions"] == 10
     assert abs(cli["fusion"]["crowding"] - m["derived"]["crowding"]) < 1e-12 and abs(cli["market"]["pct_change"] - m["derived"]["pct_change"]) < 1e-12
+    # the compiled-host twin: host_demo --analyze (C++ PostAnalyzer port + fusion functions of openintel_host.hpp)
+    from openintel_b200.host import build as host_build
+    demo = host_build.build()[1]
+    cpp = subprocess.run([demo, "--analyze", db, repr(m["last_price"]), repr(m["previous_close"]), str(m["volume"]), str(m["avg_volume"]),
+                          repr(m["iv_rank"])], capture_output=True, text=True, timeout=120)
+    assert cpp.returncode == 0, cpp.stderr[-2000:]
+    f = cpp.stdout.split()
+    assert f[0] == "report" and [int(x) for x in f[1:5]] == [10, d["bullish"], d["bearish"], d["neutral"]]
+    assert float(f[5]) == d["net_sentiment"] and float(f[6]) == d["speculation_index"]
+    assert abs(float(f[7]) - m["derived"]["crowding"]) < 1e-12 and f[8] == "ConfirmingBullish" and f[9] == "Medium"
+    solo = subprocess.run([demo, "--analyze", db], capture_output=True, text=True, timeout=120)
+    assert solo.returncode == 0 and solo.stdout.split()[8] == "Quiet"
